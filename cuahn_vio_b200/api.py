@@ -1,0 +1,279 @@
+"""ctypes binding of libuahn.so (include/uahn.h) and a Python mirror of `pytorch::HomographyNet`.
+
+This is the host-side surface for tests and bench.py.  There is no CPU fallback: if the CUDA
+library cannot be loaded or no sm_100 device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+IMG_H, IMG_W = 224, 320
+MASK_BYTES_PER_PAIR = 2 * 16 * (5120 + 256)
+VARIANTS = {"full": 0, "prior3": 1, "prior2": 2, "prior1": 3}
+PRECISIONS = {"fp32": 0, "bf16": 1}
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libuahn.so")
+EXPORTED_SYMBOLS = [
+    "uahn_create", "uahn_destroy", "uahn_last_error", "uahn_load_image", "uahn_infer", "uahn_infer_batch",
+    "uahn_infer_batch_device", "uahn_synchronize", "uahn_stream", "uahn_launch_count",
+    "uahn_latest_inference_time", "uahn_image_count", "uahn_philox_keep_masks", "uahn_stage_dlt",
+    "uahn_stage_warp", "uahn_debug_read",
+]
+
+
+class UahnError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [("weights_path", C.c_char_p), ("variant", C.c_int), ("show_error", C.c_int), ("precision", C.c_int),
+                ("device", C.c_int), ("max_batch", C.c_int), ("stream", C.c_void_p)]
+
+
+class _Rng(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("first_pair_index", C.c_uint64), ("keep_masks", C.c_void_p)]
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """Load libuahn.so (building is `python -m cuahn_vio_b200.build` / `__graft_entry__.build()`)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or _LIB_PATH
+    if not os.path.exists(p):
+        raise UahnError(f"{p} not found: build it first (python cuahn_vio_b200/build.py); there is no CPU fallback")
+    lib = C.CDLL(p)
+    vp, i, u64, dbl = C.c_void_p, C.c_int, C.c_uint64, C.c_double
+    lib.uahn_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
+    lib.uahn_create.restype = i
+    lib.uahn_destroy.argtypes = [vp]
+    lib.uahn_destroy.restype = None
+    lib.uahn_last_error.argtypes = [vp]
+    lib.uahn_last_error.restype = C.c_char_p
+    lib.uahn_load_image.argtypes = [vp, vp, i, i, C.c_size_t, dbl]
+    lib.uahn_load_image.restype = i
+    lib.uahn_infer.argtypes = [vp, vp, C.POINTER(_Rng), vp, vp, vp]
+    lib.uahn_infer.restype = i
+    for f in (lib.uahn_infer_batch, lib.uahn_infer_batch_device):
+        f.argtypes = [vp, i, vp, vp, vp, C.POINTER(_Rng), vp, vp, vp]
+        f.restype = i
+    lib.uahn_synchronize.argtypes = [vp]
+    lib.uahn_synchronize.restype = i
+    lib.uahn_stream.argtypes = [vp]
+    lib.uahn_stream.restype = vp
+    lib.uahn_launch_count.argtypes = [vp]
+    lib.uahn_launch_count.restype = u64
+    lib.uahn_latest_inference_time.argtypes = [vp]
+    lib.uahn_latest_inference_time.restype = dbl
+    lib.uahn_image_count.argtypes = [vp]
+    lib.uahn_image_count.restype = i
+    lib.uahn_philox_keep_masks.argtypes = [u64, u64, vp]
+    lib.uahn_philox_keep_masks.restype = i
+    lib.uahn_stage_dlt.argtypes = [vp, i, vp, vp]
+    lib.uahn_stage_dlt.restype = i
+    lib.uahn_stage_warp.argtypes = [vp, i, vp, vp, vp, vp, vp]
+    lib.uahn_stage_warp.restype = i
+    lib.uahn_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+    lib.uahn_debug_read.restype = C.c_long
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))   # raw address (e.g. torch tensor.data_ptr())
+
+
+def philox_keep_masks(seed: int, pair_index: int) -> np.ndarray:
+    """Host replica of the in-kernel mask generator → uint8 [2, 16, 5376] (1 = kept)."""
+    out = np.empty((2, 16, 5120 + 256), np.uint8)
+    rc = load_library().uahn_philox_keep_masks(seed, pair_index, _ptr(out))
+    if rc:
+        raise UahnError(f"uahn_philox_keep_masks rc={rc}")
+    return out
+
+
+def pack_keep_masks(masks) -> np.ndarray:
+    """(m1[16,5120], m2[16,256], u1, u2) float {0,1/0.95} tensors → explicit keep-mask bytes [2,16,5376]."""
+    m1, m2, u1, u2 = [np.asarray(m) != 0 for m in masks]
+    return np.ascontiguousarray(np.stack([np.concatenate([m1, m2], 1), np.concatenate([u1, u2], 1)]).astype(np.uint8))
+
+
+class Uahn:
+    """Thin RAII wrapper over a uahn_handle."""
+
+    def __init__(self, weights_path: str, variant: str = "prior3", show_error: bool = False, precision: str = "fp32",
+                 device: int = 0, max_batch: int = 1, stream: int | None = None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.variant, self.show_error, self.precision, self.max_batch = variant, show_error, precision, max_batch
+        cfg = _Config(os.fsencode(weights_path), VARIANTS[variant], int(show_error), PRECISIONS[precision], device,
+                      max_batch, stream)
+        rc = self._lib.uahn_create(C.byref(cfg), C.byref(self._h))
+        if rc:
+            msg = self._lib.uahn_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise UahnError(f"uahn_create failed ({rc}): {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.uahn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc < 0:
+            raise UahnError(f"rc={rc}: {self._lib.uahn_last_error(self._h).decode()}")
+        return rc
+
+    @staticmethod
+    def _rng(seed, first_pair, masks):
+        return _Rng(seed, first_pair, _ptr(masks).value if masks is not None else None)
+
+    # -- reference call surface ----------------------------------------------------------------------
+    def load_image(self, img: np.ndarray, time_stamp: float = 0.0):
+        img = np.ascontiguousarray(img, np.uint8)
+        self._check(self._lib.uahn_load_image(self._h, _ptr(img), img.shape[0], img.shape[1], img.strides[0], time_stamp))
+
+    def infer(self, prior_px=None, seed: int = 0, pair_index: int = 0, keep_masks: np.ndarray | None = None,
+              want_error: bool = False):
+        prior = None if prior_px is None else np.ascontiguousarray(prior_px, np.float64).reshape(8)
+        mean, cov = np.empty(8, np.float64), np.empty((8, 8), np.float64)
+        err = np.empty((IMG_H, IMG_W), np.uint8) if want_error else None
+        rng = self._rng(seed, pair_index, keep_masks)
+        self._check(self._lib.uahn_infer(self._h, _ptr(prior), C.byref(rng), _ptr(mean), _ptr(cov), _ptr(err)))
+        return mean, cov, err
+
+    def infer_batch(self, prev: np.ndarray, curr: np.ndarray, prior: np.ndarray | None = None, seed: int = 0,
+                    first_pair: int = 0, keep_masks: np.ndarray | None = None, want_error: bool = False):
+        n = prev.shape[0]
+        prev, curr = np.ascontiguousarray(prev, np.uint8), np.ascontiguousarray(curr, np.uint8)
+        prior = None if prior is None else np.ascontiguousarray(prior, np.float32).reshape(n, 8)
+        if keep_masks is not None:
+            keep_masks = np.ascontiguousarray(keep_masks, np.uint8)
+            assert keep_masks.size == n * MASK_BYTES_PER_PAIR
+        mean, cov = np.empty((n, 8), np.float32), np.empty((n, 8, 8), np.float32)
+        err = np.empty((n, IMG_H, IMG_W), np.float32) if want_error else None
+        rng = self._rng(seed, first_pair, keep_masks)
+        self._check(self._lib.uahn_infer_batch(self._h, n, _ptr(prev), _ptr(curr), _ptr(prior), C.byref(rng), _ptr(mean),
+                                               _ptr(cov), _ptr(err)))
+        return mean, cov, err
+
+    def infer_batch_ptrs(self, n, prev, curr, prior, mean, cov, err=None, seed=0, first_pair=0, device=True):
+        """Raw-address form (device pointers by default): asynchronous on the handle's stream."""
+        rng = _Rng(seed, first_pair, None)
+        f = self._lib.uahn_infer_batch_device if device else self._lib.uahn_infer_batch
+        self._check(f(self._h, n, _ptr(prev), _ptr(curr), _ptr(prior), C.byref(rng), _ptr(mean), _ptr(cov), _ptr(err)))
+
+    def synchronize(self):
+        self._check(self._lib.uahn_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.uahn_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.uahn_launch_count(self._h))
+
+    @property
+    def img_counter(self) -> int:
+        return int(self._lib.uahn_image_count(self._h))
+
+    @property
+    def latest_inference_time(self) -> float:
+        return float(self._lib.uahn_latest_inference_time(self._h))
+
+    # -- stage entry points --------------------------------------------------------------------------
+    def stage_dlt(self, offsets: np.ndarray) -> np.ndarray:
+        off = np.ascontiguousarray(offsets, np.float32).reshape(-1, 8)
+        out = np.empty((off.shape[0], 3, 3), np.float32)
+        self._check(self._lib.uahn_stage_dlt(self._h, off.shape[0], _ptr(off), _ptr(out)))
+        return out
+
+    def stage_warp(self, img: np.ndarray, H: np.ndarray):
+        img = np.ascontiguousarray(img, np.uint8).reshape(-1, IMG_H, IMG_W)
+        H = np.ascontiguousarray(H, np.float32).reshape(-1, 9)
+        n = img.shape[0]
+        out = np.empty((n, IMG_H, IMG_W), np.float32)
+        ix, iy = np.empty((n, IMG_H, IMG_W), np.int16), np.empty((n, IMG_H, IMG_W), np.int16)
+        self._check(self._lib.uahn_stage_warp(self._h, n, _ptr(img), _ptr(H), _ptr(out), _ptr(ix), _ptr(iy)))
+        return out, ix, iy
+
+    def debug_read(self, what: str, shape) -> np.ndarray:
+        out = np.empty(shape, np.float32)
+        got = self._check(self._lib.uahn_debug_read(self._h, what.encode(), _ptr(out), out.size))
+        if got != out.size:
+            raise UahnError(f"debug_read({what}): got {got} floats, expected {out.size}")
+        return out
+
+
+class HomographyNet:
+    """Python mirror of `pytorch::HomographyNet` (HomographyNet.h:23-67) over the C ABI.
+
+    Same members and argument meaning: ctor(model path → weights file, iterative model path, use_prior,
+    num_of_iteration, show_imgs); load_current_img; network_inference(prior_4pt_offset_vec, iteration);
+    get_pred_mean / get_pred_Cov / get_latest_inference_time; img_counter.  Variant selection follows the
+    reference's file-name convention (`_showError` substring, HomographyNet.cpp:96-100).
+    """
+
+    def __init__(self, network_model_path: str, network_model_iterative_path: str = "", use_prior: bool = True,
+                 num_of_iteration: int = 1, show_imgs: bool = False, precision: str = "bf16", device: int = 0,
+                 iterative_variant: str = "prior2"):
+        self.use_prior = use_prior
+        self.show_error = "_showError" in network_model_path
+        self.show_imgs = show_imgs
+        self._main = Uahn(network_model_path, "prior3" if use_prior else "full", self.show_error, precision, device, 1)
+        self._iter = None
+        if num_of_iteration > 1:
+            self._iter = Uahn(network_model_iterative_path or network_model_path, iterative_variant,
+                              "_showError" in (network_model_iterative_path or network_model_path), precision, device, 1)
+        self._mean = np.zeros(8)
+        self._cov = np.zeros((8, 8))
+        self.error_map = None
+        self.seed = 0
+        self._calls = 0
+
+    @property
+    def img_counter(self) -> int:
+        return self._main.img_counter
+
+    def load_current_img(self, img: np.ndarray, time_stamp: float):
+        self._main.load_image(img, time_stamp)
+        if self._iter is not None:
+            self._iter.load_image(img, time_stamp)
+
+    def network_inference(self, prior_4pt_offset_vec, iteration: int = 0):
+        if self.img_counter < 2:                       # HomographyNet.cpp:155-158: message, outputs untouched
+            print("HNet cannot inference! Only has one image!")
+            return
+        net = self._main if iteration == 0 or self._iter is None else self._iter
+        self._calls += 1
+        mean, cov, err = net.infer(prior_4pt_offset_vec if self.use_prior else None, seed=self.seed,
+                                   pair_index=self._calls, want_error=self.show_imgs and net.show_error)
+        self._mean, self._cov, self.error_map = mean, cov, err
+
+    def get_pred_mean(self):
+        return self._mean.copy()
+
+    def get_pred_Cov(self):
+        return self._cov.copy()
+
+    def get_latest_inference_time(self) -> float:
+        return self._main.latest_inference_time

@@ -1,0 +1,97 @@
+// Shared definitions for the UAHN sm_100a kernels and the host engine.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace uahn {
+
+constexpr int IMG_H = 224;
+constexpr int IMG_W = 320;
+constexpr int IMG_PIXELS = IMG_H * IMG_W;
+constexpr int MC = 16;          // MC-dropout samples (model_to_trace.py:202)
+constexpr int FC_IN = 5120;     // 256 x 4 x 5  (model_to_trace.py:89)
+constexpr int FC_HID = 256;     // model_to_trace.py:224
+constexpr float LRELU_SLOPE = 0.1f;
+constexpr float KEEP_SCALE = 1.0f / 0.95f;  // nn.Dropout(p=0.05) in train mode
+constexpr int MASK_ROW = FC_IN + FC_HID;    // explicit keep-mask bytes per (head, sample)
+
+// Activation tensors are zero-haloed NHWC ("padded NHWC"): [n][ph + H + ph][pwl + W + pwr][C].
+// The halo is the consuming convolution's zero padding, materialised once (cudaMemset at
+// allocation; kernels only ever write the interior), so conv producers need no bounds checks.
+struct Tensor {
+  void* p = nullptr;
+  int N = 0, H = 0, W = 0, C = 0;
+  int ph = 0, pwl = 0, pwr = 0;
+  int Hp = 0, Wp = 0;        // padded extents
+  long long pitch_n = 0;     // elements between consecutive images
+  __host__ __device__ long long pitch_y() const { return (long long)Wp * C; }
+  __host__ __device__ long long off(int n, int y, int x, int c = 0) const {
+    return (long long)n * pitch_n + ((long long)(y + ph) * Wp + (x + pwl)) * C + c;
+  }
+};
+
+// One convolution (or dense layer seen as a 1x1 convolution over a 1x1 image).
+struct ConvGeom {
+  int M;                 // output pixels over the whole batch = N * Ho * Wo
+  int Ho, Wo;
+  int Cin, Cout;
+  int KH, KW, stride;
+  int K;                 // KH * KW * Cin, ordered (ky, kx, c) — c fastest
+  long long in_pitch_n, in_pitch_y;    // elements
+  long long in_origin;   // element offset of tap (ky=0,kx=0,c=0) of output pixel (0,0) in image 0
+  long long out_pitch_n, out_pitch_y;  // elements
+  long long out_origin;  // element offset of output pixel (0,0), channel 0 in image 0
+  int act;               // 1: LeakyReLU(0.1), 0: identity
+};
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : v * LRELU_SLOPE; }
+
+// ---- Philox4x32-10 (host + device): the in-kernel MC-dropout mask source ------------------------------
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    unsigned long long p = (unsigned long long)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+  }
+  __host__ __device__ static inline void gen(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                             uint32_t out[4]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t h0, l0, h1, l1;
+      mulhilo(M0, c0, h0, l0);
+      mulhilo(M1, c2, h1, l1);
+      uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+};
+// A unit is dropped iff its 16-bit draw < DROP_THRESH_16  (p = 3277/65536 = 0.0500031).
+constexpr uint32_t DROP_THRESH_16 = 3277u;
+// keep decision for (pair, head, layer, sample, index): one Philox block serves 8 consecutive indices.
+__host__ __device__ inline uint32_t philox_keep8(uint64_t seed, uint64_t pair, int head, int layer, int sample,
+                                                 int idx8) {
+  uint32_t r[4];
+  Philox::gen(seed, (uint32_t)idx8, (uint32_t)(sample | (head << 8) | (layer << 16)), (uint32_t)pair,
+              (uint32_t)(pair >> 32), r);
+  uint32_t bits = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bits |= ((r[i] & 0xFFFFu) >= DROP_THRESH_16 ? 1u : 0u) << (2 * i);
+    bits |= ((r[i] >> 16) >= DROP_THRESH_16 ? 1u : 0u) << (2 * i + 1);
+  }
+  return bits;  // bit j = keep(index idx8*8 + j)
+}
+
+}  // namespace uahn

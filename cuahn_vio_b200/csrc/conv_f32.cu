@@ -1,0 +1,123 @@
+// fp32 validation-mode convolution: Conv2d(+bias) -> LeakyReLU(0.1)  (model_to_trace.py:7-15) as a SIMT
+// implicit GEMM with true fp32 FFMA accumulation (no TF32 — SURVEY §7: the 1e-3 px budget has only a
+// 5-10x margin over fp32 noise).  M = output pixels of the whole batch, N = Cout, K = KH*KW*Cin.
+// Inputs/outputs are zero-haloed NHWC fp32 tensors, so the k-th im2col element of a pixel is simply
+// in[row_base(pixel) + koff(k)] with no bounds test.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace uahn {
+namespace {
+
+constexpr int BK = 16;
+constexpr int CONV_THREADS = 256;
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(CONV_THREADS) conv_f32_kernel(const float* __restrict__ in,
+                                                                const float* __restrict__ wk,  // [K][Cout]
+                                                                const float* __restrict__ bias, float* __restrict__ out,
+                                                                ConvGeom g) {
+  static_assert((BM / TM) * (BN / TN) == CONV_THREADS, "thread tiling");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* As = reinterpret_cast<float*>(smem_raw);              // [BK][BM]
+  float* Bs = As + BK * BM;                                    // [BK][BN]
+  long long* rowbase = reinterpret_cast<long long*>(Bs + BK * BN);   // [BM]
+  int* koff = reinterpret_cast<int*>(rowbase + BM);            // [K]
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int run = g.KW * g.Cin;
+  for (int k = tid; k < g.K; k += CONV_THREADS) {
+    const int ky = k / run;
+    koff[k] = (int)(ky * g.in_pitch_y + (k - ky * run));
+  }
+  const int hw = g.Ho * g.Wo;
+  for (int m = tid; m < BM; m += CONV_THREADS) {
+    const int gm = min(m0 + m, g.M - 1);
+    const int n = gm / hw, r = gm - n * hw;
+    const int oy = r / g.Wo, ox = r - oy * g.Wo;
+    rowbase[m] = g.in_origin + (long long)n * g.in_pitch_n + (long long)(oy * g.stride) * g.in_pitch_y +
+                 (long long)(ox * g.stride) * g.Cin;
+  }
+  __syncthreads();
+
+  constexpr int TX = BN / TN;
+  const int tx = tid % TX, ty = tid / TX;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    for (int idx = tid; idx < BM * BK; idx += CONV_THREADS) {
+      const int m = idx % BM, kk = idx / BM;
+      const int k = k0 + kk;
+      As[kk * BM + m] = (k < g.K) ? __ldg(in + rowbase[m] + koff[k]) : 0.f;
+    }
+    for (int idx = tid; idx < BN * BK; idx += CONV_THREADS) {
+      const int nn = idx % BN, kk = idx / BN;
+      const int k = k0 + kk;
+      Bs[kk * BN + nn] = (k < g.K && n0 + nn < g.Cout) ? __ldg(wk + (size_t)k * g.Cout + n0 + nn) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk * BM + ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk * BN + tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
+    if (gm >= g.M) continue;
+    const int n = gm / hw, r = gm - n * hw;
+    const int oy = r / g.Wo, ox = r - oy * g.Wo;
+    float* o = out + g.out_origin + (long long)n * g.out_pitch_n + (long long)oy * g.out_pitch_y +
+               (long long)ox * g.Cout;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int c = n0 + tx * TN + j;
+      if (c < g.Cout) {
+        float v = acc[i][j] + (bias ? __ldg(bias + c) : 0.f);
+        o[c] = g.act ? lrelu(v) : v;
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+cudaError_t launch_cfg(const float* in, const float* wk, const float* bias, float* out, const ConvGeom& g,
+                       cudaStream_t st) {
+  const size_t smem = (size_t)(BK * BM + BK * BN) * 4 + (size_t)BM * 8 + (size_t)g.K * 4;
+  static size_t max_set = 0;
+  if (smem > 48 * 1024 && smem > max_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_f32_kernel<BM, BN, TM, TN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    max_set = smem;
+  }
+  dim3 grid((g.M + BM - 1) / BM, (g.Cout + BN - 1) / BN);
+  conv_f32_kernel<BM, BN, TM, TN><<<grid, CONV_THREADS, smem, st>>>(in, wk, bias, out, g);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_conv_f32(const float* in, const float* wk, const float* bias, float* out, const ConvGeom& g,
+                            cudaStream_t st) {
+  if (g.Cout >= 64) return launch_cfg<64, 64, 4, 4>(in, wk, bias, out, g, st);
+  if (g.Cout >= 32) return launch_cfg<128, 32, 4, 4>(in, wk, bias, out, g, st);
+  if (g.Cout >= 16) return launch_cfg<256, 16, 4, 4>(in, wk, bias, out, g, st);
+  return launch_cfg<256, 8, 4, 2>(in, wk, bias, out, g, st);
+}
+
+}  // namespace uahn

@@ -1,0 +1,690 @@
+// Host engine + C ABI (include/uahn.h) of the B200-native UAHN forward.
+// Stage schedule follows combined_stu_model.forward / Down_Net_3blocks.forward / HomoNet_last_block.forward
+// (reference model_to_trace.py:124-193, 258-282, 299-330); see DESIGN.md for the kernel map.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/uahn.h"
+#include "common.cuh"
+#include "conv_bf16.h"
+#include "kernels.h"
+
+using namespace uahn;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostTensor {
+  std::vector<int> dims;
+  std::vector<float> data;
+  size_t numel() const {
+    size_t n = 1;
+    for (int d : dims) n *= d;
+    return n;
+  }
+};
+
+bool load_weight_file(const char* path, std::map<std::string, HostTensor>& out, std::string& err) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { err = std::string("cannot open weights file: ") + path; return false; }
+  char magic[8];
+  uint32_t count = 0;
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "UAHNWTS1", 8) != 0 || fread(&count, 4, 1, f) != 1) {
+    fclose(f); err = "bad weights file header"; return false;
+  }
+  for (uint32_t i = 0; i < count; ++i) {
+    uint32_t nl = 0, nd = 0;
+    if (fread(&nl, 4, 1, f) != 1 || nl > 256) { fclose(f); err = "bad tensor name"; return false; }
+    std::string name(nl, '\0');
+    if (fread(&name[0], 1, nl, f) != nl || fread(&nd, 4, 1, f) != 1 || nd > 4) { fclose(f); err = "bad tensor header"; return false; }
+    HostTensor t;
+    t.dims.resize(nd);
+    for (uint32_t d = 0; d < nd; ++d) {
+      uint32_t v;
+      if (fread(&v, 4, 1, f) != 1) { fclose(f); err = "bad dims"; return false; }
+      t.dims[d] = (int)v;
+    }
+    t.data.resize(t.numel());
+    if (fread(t.data.data(), 4, t.data.size(), f) != t.data.size()) { fclose(f); err = "truncated tensor " + name; return false; }
+    out[name] = std::move(t);
+  }
+  fclose(f);
+  return true;
+}
+
+struct LayerSpec { const char* name; int cout, cin, k, stride; };
+// model_to_trace.py:93-95,100-103,108-113,210-216
+const LayerSpec B1[] = {{"block_1_1", 128, 2, 7, 2}, {"block_1_2", 128, 128, 5, 2}, {"block_1_3", 256, 128, 3, 2}};
+const LayerSpec B2[] = {{"block_2_1", 64, 2, 7, 2}, {"block_2_2", 128, 64, 5, 2}, {"block_2_3", 256, 128, 3, 2}, {"block_2_4", 256, 256, 3, 2}};
+const LayerSpec B3[] = {{"block_3_0", 16, 2, 7, 1}, {"block_3_1", 32, 16, 5, 2}, {"block_3_2", 64, 32, 3, 2}, {"block_3_3", 128, 64, 3, 2}, {"block_3_4", 256, 128, 3, 2}, {"block_3_5", 256, 256, 3, 2}};
+const LayerSpec B4[] = {{"block_4_0", 8, 2, 7, 1}, {"block_4_1", 16, 8, 5, 2}, {"block_4_2", 32, 16, 3, 2}, {"block_4_3", 64, 32, 3, 2}, {"block_4_4", 128, 64, 3, 2}, {"block_4_5", 256, 128, 3, 2}, {"block_4_6", 256, 256, 3, 2}};
+const char* P1 = "model_part1.";
+const char* P4 = "model_last_block_list.0.";
+
+struct Layer {
+  LayerSpec spec;
+  int Hin, Win, Ho, Wo;
+  Tensor in, out;
+  float* w_f32 = nullptr;   // [K][Cout], k = (ky*KW + kx)*Cin + c
+  float* bias = nullptr;
+  ConvBf16Weights wb;       // bf16 tcgen05 operand image (precision BF16 only)
+};
+
+struct Block {
+  int id = 0, pool = 1;
+  bool active = false;
+  Tensor x;                 // 2-channel conv input
+  std::vector<Layer> layers;
+  float* W8 = nullptr;      // [8][5120] permuted to NHWC feature order (blocks 1-3)
+  float* b8 = nullptr;
+};
+
+}  // namespace
+
+struct uahn_handle {
+  uahn_config cfg{};
+  std::string last_error;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool bf16 = false;
+  size_t es = 4;
+  int cap = 0;
+  uint64_t launches = 0;
+  std::vector<void*> allocs;
+  Block blocks[5];
+  // block-4 head
+  float *W1m = nullptr, *b1m = nullptr, *W1u = nullptr, *b1u = nullptr;       // [5120][256] fp32 (k' order)
+  ConvBf16Weights W1m_b, W1u_b;
+  float *W2m = nullptr, *b2m = nullptr, *W2u = nullptr, *b2u = nullptr;
+  void* mcA = nullptr;    // [2][cap][16][5120] T
+  void* hid = nullptr;    // [2][cap][16][256] T
+  float* Hb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // cumulative H after prior(0)/block1..3 ; [4] unused
+  float* Htot = nullptr;
+  float* dblk[4] = {nullptr, nullptr, nullptr, nullptr};          // regressed offsets of blocks 1..3
+  float *mc_mean = nullptr, *mc_logvar = nullptr;
+  // staging for the host-pointer entry points
+  uint8_t *d_prev = nullptr, *d_curr = nullptr, *d_masks = nullptr;
+  float *d_prior = nullptr, *d_mean = nullptr, *d_cov = nullptr, *d_err = nullptr;
+  // streaming (load_image / infer) state: 2-slot ring
+  uint8_t* d_ring = nullptr;
+  uint8_t* h_img = nullptr;   // pinned
+  float* h_out = nullptr;     // pinned 72 floats (+ err map)
+  int ring_curr = 0;
+  int img_counter = 0;
+  double latest_time = -1.0;
+  int last_n = 0;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error = buf;
+    return code;
+  }
+};
+
+#define CK(expr)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e__ = (expr);                                                                             \
+    if (e__ != cudaSuccess) return h->fail(UAHN_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define LAUNCH(expr)  \
+  do {                \
+    CK(expr);         \
+    ++h->launches;    \
+  } while (0)
+
+namespace {
+
+template <typename T>
+int dev_alloc(uahn_handle* h, T** p, size_t count, bool zero = true) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, count * sizeof(T) + 4096));
+  if (zero) CK(cudaMemset(q, 0, count * sizeof(T) + 4096));
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return UAHN_OK;
+}
+
+int upload(uahn_handle* h, float** dst, const std::vector<float>& v) {
+  int rc = dev_alloc(h, dst, v.size(), false);
+  if (rc) return rc;
+  CK(cudaMemcpy(*dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  return UAHN_OK;
+}
+
+int make_tensor(uahn_handle* h, Tensor& t, int N, int H, int W, int C, int pad) {
+  t.N = N; t.H = H; t.W = W; t.C = C;
+  t.ph = pad; t.pwl = pad; t.pwr = pad ? pad + 8 : 0;
+  t.Hp = H + 2 * pad;
+  t.Wp = W + t.pwl + t.pwr;
+  if (pad) t.Wp = (t.Wp + 7) / 8 * 8;
+  t.pitch_n = ((long long)t.Hp * t.Wp * C + 63) / 64 * 64;
+  uint8_t* p = nullptr;
+  int rc = dev_alloc(h, &p, (size_t)N * t.pitch_n * h->es);
+  t.p = p;
+  return rc;
+}
+
+ConvGeom make_geom(const Layer& L, int n) {
+  ConvGeom g{};
+  const int p = (L.spec.k - 1) / 2;
+  g.Ho = L.Ho; g.Wo = L.Wo; g.M = n * L.Ho * L.Wo;
+  g.Cin = L.spec.cin; g.Cout = L.spec.cout; g.KH = g.KW = L.spec.k; g.stride = L.spec.stride;
+  g.K = L.spec.k * L.spec.k * L.spec.cin;
+  g.in_pitch_n = L.in.pitch_n; g.in_pitch_y = L.in.pitch_y();
+  g.in_origin = L.in.off(0, -p, -p, 0);
+  g.out_pitch_n = L.out.pitch_n; g.out_pitch_y = L.out.pitch_y();
+  g.out_origin = L.out.off(0, 0, 0, 0);
+  g.act = 1;
+  return g;
+}
+
+ConvGeom dense_geom(int rows, int K, int N, int act) {   // Linear as a 1x1 conv over 1x1 images
+  ConvGeom g{};
+  g.Ho = g.Wo = 1; g.M = rows; g.Cin = K; g.Cout = N; g.KH = g.KW = 1; g.stride = 1; g.K = K;
+  g.in_pitch_n = K; g.in_pitch_y = K; g.in_origin = 0;
+  g.out_pitch_n = N; g.out_pitch_y = N; g.out_origin = 0;
+  g.act = act;
+  return g;
+}
+
+const HostTensor* find(const std::map<std::string, HostTensor>& w, const std::string& key, std::vector<int> dims,
+                       std::string& err) {
+  auto it = w.find(key);
+  if (it == w.end()) { err = "missing tensor " + key; return nullptr; }
+  if (it->second.dims != dims) { err = "shape mismatch for " + key; return nullptr; }
+  return &it->second;
+}
+
+// [8][5120] or [256][5120] with the 5120 axis in NCHW order (c*20+hw) -> NHWC order (hw*256+c)
+std::vector<float> permute_fc_in(const HostTensor& t) {
+  const int rows = t.dims[0];
+  std::vector<float> o((size_t)rows * FC_IN);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < 256; ++c)
+      for (int hw = 0; hw < 20; ++hw) o[(size_t)r * FC_IN + hw * 256 + c] = t.data[(size_t)r * FC_IN + c * 20 + hw];
+  return o;
+}
+
+int build_block(uahn_handle* h, const std::map<std::string, HostTensor>& w, int id, const LayerSpec* specs, int nl,
+                int pool) {
+  Block& B = h->blocks[id];
+  B.id = id; B.pool = pool; B.active = true;
+  const char* pre = id == 4 ? P4 : P1;
+  int H = IMG_H / pool, W = IMG_W / pool;
+  int rc = make_tensor(h, B.x, h->cap, H, W, 2, (specs[0].k - 1) / 2);
+  if (rc) return rc;
+  Tensor cur = B.x;
+  std::string err;
+  for (int i = 0; i < nl; ++i) {
+    Layer L;
+    L.spec = specs[i];
+    const int p = (L.spec.k - 1) / 2;
+    L.Hin = H; L.Win = W;
+    L.Ho = (H + 2 * p - L.spec.k) / L.spec.stride + 1;
+    L.Wo = (W + 2 * p - L.spec.k) / L.spec.stride + 1;
+    L.in = cur;
+    const int next_pad = i + 1 < nl ? (specs[i + 1].k - 1) / 2 : 0;
+    rc = make_tensor(h, L.out, h->cap, L.Ho, L.Wo, L.spec.cout, next_pad);
+    if (rc) return rc;
+    const std::string key = std::string(pre) + L.spec.name + ".0.";
+    const HostTensor* wt = find(w, key + "weight", {L.spec.cout, L.spec.cin, L.spec.k, L.spec.k}, err);
+    const HostTensor* bt = wt ? find(w, key + "bias", {L.spec.cout}, err) : nullptr;
+    if (!bt) return h->fail(UAHN_ERR_WEIGHTS, "%s", err.c_str());
+    const int K = L.spec.k * L.spec.k * L.spec.cin, kk = L.spec.k;
+    std::vector<float> wk((size_t)K * L.spec.cout);
+    for (int co = 0; co < L.spec.cout; ++co)
+      for (int c = 0; c < L.spec.cin; ++c)
+        for (int ky = 0; ky < kk; ++ky)
+          for (int kx = 0; kx < kk; ++kx)
+            wk[(size_t)((ky * kk + kx) * L.spec.cin + c) * L.spec.cout + co] =
+                wt->data[(((size_t)co * L.spec.cin + c) * kk + ky) * kk + kx];
+    if (h->bf16) {
+      if (conv_bf16_prepare(L.wb, wk, bt->data, make_geom(L, 1), L.in, L.out, h->allocs, err))
+        return h->fail(UAHN_ERR_UNSUPPORTED, "%s: %s", L.spec.name, err.c_str());
+    } else {
+      if ((rc = upload(h, &L.w_f32, wk))) return rc;
+    }
+    if ((rc = upload(h, &L.bias, bt->data))) return rc;
+    B.layers.push_back(L);
+    cur = L.out;
+    H = L.Ho; W = L.Wo;
+  }
+  if (H != 4 || W != 5 || specs[nl - 1].cout != 256) return h->fail(UAHN_ERR_INVALID, "block %d does not end at 256x4x5", id);
+  if (id != 4) {
+    const std::string key = std::string(P1) + "fc_block_" + std::to_string(id) + ".";
+    const HostTensor* wt = find(w, key + "weight", {8, FC_IN}, err);
+    const HostTensor* bt = wt ? find(w, key + "bias", {8}, err) : nullptr;
+    if (!bt) return h->fail(UAHN_ERR_WEIGHTS, "%s", err.c_str());
+    if ((rc = upload(h, &B.W8, permute_fc_in(*wt)))) return rc;
+    if ((rc = upload(h, &B.b8, bt->data))) return rc;
+  }
+  return UAHN_OK;
+}
+
+int build_head(uahn_handle* h, const std::map<std::string, HostTensor>& w) {
+  std::string err;
+  int rc;
+  struct { const char* name; float** W1; float** b1; float** W2; float** b2; ConvBf16Weights* wb; } heads[2] = {
+      {"fc_block_4_mean", &h->W1m, &h->b1m, &h->W2m, &h->b2m, &h->W1m_b},
+      {"fc_block_4_uncertainty", &h->W1u, &h->b1u, &h->W2u, &h->b2u, &h->W1u_b}};
+  for (auto& hd : heads) {
+    const std::string key = std::string(P4) + hd.name;
+    const HostTensor* w1 = find(w, key + ".1.weight", {FC_HID, FC_IN}, err);
+    const HostTensor* b1 = w1 ? find(w, key + ".1.bias", {FC_HID}, err) : nullptr;
+    const HostTensor* w2 = b1 ? find(w, key + ".4.weight", {8, FC_HID}, err) : nullptr;
+    const HostTensor* b2 = w2 ? find(w, key + ".4.bias", {8}, err) : nullptr;
+    if (!b2) return h->fail(UAHN_ERR_WEIGHTS, "%s", err.c_str());
+    std::vector<float> perm = permute_fc_in(*w1);           // [256][5120 NHWC]
+    std::vector<float> wk((size_t)FC_IN * FC_HID);          // [K][Cout]
+    for (int j = 0; j < FC_HID; ++j)
+      for (int k = 0; k < FC_IN; ++k) wk[(size_t)k * FC_HID + j] = perm[(size_t)j * FC_IN + k];
+    if (h->bf16) {
+      Tensor tin{}, tout{};
+      if (conv_bf16_prepare(*hd.wb, wk, b1->data, dense_geom(1, FC_IN, FC_HID, 1), tin, tout, h->allocs, err))
+        return h->fail(UAHN_ERR_UNSUPPORTED, "%s: %s", hd.name, err.c_str());
+    } else {
+      if ((rc = upload(h, hd.W1, wk))) return rc;
+    }
+    if ((rc = upload(h, hd.b1, b1->data))) return rc;
+    if ((rc = upload(h, hd.W2, w2->data))) return rc;
+    if ((rc = upload(h, hd.b2, b2->data))) return rc;
+  }
+  return UAHN_OK;
+}
+
+template <typename T>
+int run_conv(uahn_handle* h, Layer& L, int n) {
+  ConvGeom g = make_geom(L, n);
+  if constexpr (sizeof(T) == 4) {
+    LAUNCH(launch_conv_f32((const float*)L.in.p, L.w_f32, L.bias, (float*)L.out.p, g, h->stream));
+  } else {
+    LAUNCH(launch_conv_bf16(L.wb, L.in.p, L.bias, L.out.p, g, h->stream));
+  }
+  return UAHN_OK;
+}
+
+template <typename T>
+int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior, const uahn_rng* rng,
+            const uint8_t* d_masks, float* mean, float* cov, float* err) {
+  cudaStream_t st = h->stream;
+  const int variant = h->cfg.variant;
+  const float* Hcur = nullptr;
+  int rc;
+  if (variant != UAHN_VARIANT_FULL) {
+    if (!prior) return h->fail(UAHN_ERR_INVALID, "this variant needs a prior");
+    LAUNCH(launch_dlt(n, prior, nullptr, h->Hb[0], st));                   // model_to_trace.py:129-130
+    Hcur = h->Hb[0];
+  }
+  for (int b = 1; b <= 3; ++b) {
+    Block& B = h->blocks[b];
+    if (!B.active) continue;
+    // block 1 sees the raw current image (model_to_trace.py:138-139); blocks 2,3 the warped one (:154,172)
+    LAUNCH(launch_warp_concat_pool<T>(prev, curr, b == 1 ? nullptr : Hcur, B.x, B.pool, n, st));
+    for (Layer& L : B.layers)
+      if ((rc = run_conv<T>(h, L, n))) return rc;
+    LAUNCH(launch_fc8_dlt<T>(n, (const T*)B.layers.back().out.p, B.W8, B.b8, b == 1 ? nullptr : Hcur, h->Hb[b],
+                             h->dblk[b], st));
+    Hcur = h->Hb[b];
+  }
+  Block& B4 = h->blocks[4];
+  LAUNCH(launch_warp_concat_pool<T>(prev, curr, Hcur, B4.x, 1, n, st));     // model_to_trace.py:261-263
+  for (Layer& L : B4.layers)
+    if ((rc = run_conv<T>(h, L, n))) return rc;
+  const T* feat = (const T*)B4.layers.back().out.p;
+  const uint64_t seed = rng ? rng->seed : 0, first = rng ? rng->first_pair_index : 0;
+  LAUNCH(launch_mc_expand<T>(n, feat, (T*)h->mcA, d_masks, seed, first, st));
+  for (int head = 0; head < 2; ++head) {
+    ConvGeom g = dense_geom(n * MC, FC_IN, FC_HID, 1);
+    const T* a = (const T*)h->mcA + (size_t)head * n * MC * FC_IN;
+    T* o = (T*)h->hid + (size_t)head * n * MC * FC_HID;
+    if constexpr (sizeof(T) == 4) {
+      LAUNCH(launch_conv_f32((const float*)a, head ? h->W1u : h->W1m, head ? h->b1u : h->b1m, (float*)o, g, st));
+    } else {
+      LAUNCH(launch_conv_bf16(head ? h->W1u_b : h->W1m_b, a, head ? h->b1u : h->b1m, o, g, st));
+    }
+  }
+  const bool want_err = h->cfg.show_error && err;
+  LAUNCH(launch_mc_final<T>(n, (const T*)h->hid, h->W2m, h->b2m, h->W2u, h->b2u, Hcur, d_masks, seed, first, mean, cov,
+                            h->cfg.show_error ? h->Htot : nullptr, h->mc_mean, h->mc_logvar, st));
+  if (want_err) LAUNCH(launch_warp_plain(prev, curr, h->Htot, err, nullptr, nullptr, 1, n, st));
+  h->last_n = n;
+  return UAHN_OK;
+}
+
+int forward_any(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior,
+                const uahn_rng* rng, const uint8_t* d_masks, float* mean, float* cov, float* err) {
+  if (n <= 0 || n > h->cap) return h->fail(UAHN_ERR_INVALID, "n=%d outside [1, max_batch=%d]", n, h->cap);
+  return h->bf16 ? forward<__nv_bfloat16>(h, n, prev, curr, prior, rng, d_masks, mean, cov, err)
+                 : forward<float>(h, n, prev, curr, prior, rng, d_masks, mean, cov, err);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int uahn_create(const uahn_config* cfg, uahn_handle** out) {
+  if (!cfg || !out || !cfg->weights_path) { g_create_error = "null config / weights_path"; return UAHN_ERR_INVALID; }
+  if (cfg->variant < 0 || cfg->variant > 3 || cfg->precision < 0 || cfg->precision > 1 || cfg->max_batch < 1) {
+    g_create_error = "invalid variant / precision / max_batch";
+    return UAHN_ERR_INVALID;
+  }
+  uahn_handle* h = new uahn_handle();
+  h->cfg = *cfg;
+  h->cap = cfg->max_batch;
+  h->bf16 = cfg->precision == UAHN_PRECISION_BF16;
+  h->es = h->bf16 ? 2 : 4;
+  auto bail = [&](int rc) {
+    g_create_error = h->last_error;
+    uahn_destroy(h);
+    return rc;
+  };
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    h->fail(UAHN_ERR_CUDA, "no CUDA device: %s — this library has no CPU fallback", cudaGetErrorString(e));
+    return bail(UAHN_ERR_CUDA);
+  }
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) {
+    h->fail(UAHN_ERR_CUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e));
+    return bail(UAHN_ERR_CUDA);
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10) {
+    h->fail(UAHN_ERR_UNSUPPORTED, "device sm_%d%d: kernels are built for sm_100a only", prop.major, prop.minor);
+    return bail(UAHN_ERR_UNSUPPORTED);
+  }
+  if (cfg->stream) {
+    h->stream = (cudaStream_t)cfg->stream;
+  } else {
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+      h->fail(UAHN_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+      return bail(UAHN_ERR_CUDA);
+    }
+    h->own_stream = true;
+  }
+  std::map<std::string, HostTensor> w;
+  std::string err;
+  if (!load_weight_file(cfg->weights_path, w, err)) {
+    h->fail(UAHN_ERR_WEIGHTS, "%s", err.c_str());
+    return bail(UAHN_ERR_WEIGHTS);
+  }
+  int rc = UAHN_OK;
+  const int v = cfg->variant;
+  if (v == UAHN_VARIANT_FULL && (rc = build_block(h, w, 1, B1, 3, 8))) return bail(rc);
+  if ((v == UAHN_VARIANT_FULL || v == UAHN_VARIANT_PRIOR3) && (rc = build_block(h, w, 2, B2, 4, 4))) return bail(rc);
+  if (v != UAHN_VARIANT_PRIOR1 && (rc = build_block(h, w, 3, B3, 6, 2))) return bail(rc);
+  if ((rc = build_block(h, w, 4, B4, 7, 1))) return bail(rc);
+  if ((rc = build_head(h, w))) return bail(rc);
+  const size_t cap = h->cap;
+  uint8_t* p8 = nullptr;
+  if ((rc = dev_alloc(h, &p8, 2 * cap * MC * FC_IN * h->es))) return bail(rc);
+  h->mcA = p8;
+  if ((rc = dev_alloc(h, &p8, 2 * cap * MC * FC_HID * h->es))) return bail(rc);
+  h->hid = p8;
+  for (int i = 0; i < 4; ++i) {
+    if ((rc = dev_alloc(h, &h->Hb[i], cap * 9))) return bail(rc);
+    if ((rc = dev_alloc(h, &h->dblk[i], cap * 8))) return bail(rc);
+  }
+  if ((rc = dev_alloc(h, &h->Htot, cap * 9))) return bail(rc);
+  if ((rc = dev_alloc(h, &h->mc_mean, cap * MC * 8))) return bail(rc);
+  if ((rc = dev_alloc(h, &h->mc_logvar, cap * MC * 8))) return bail(rc);
+  if ((rc = dev_alloc(h, &h->d_prev, cap * IMG_PIXELS))) return bail(rc);
+  if ((rc = dev_alloc(h, &h->d_curr, cap * IMG_PIXELS))) return bail(rc);
+  if ((rc = dev_alloc(h, &h->d_prior, cap * 8))) return bail(rc);
+  if ((rc = dev_alloc(h, &h->d_mean, cap * 8))) return bail(rc);
+  if ((rc = dev_alloc(h, &h->d_cov, cap * 64))) return bail(rc);
+  if (cfg->show_error && (rc = dev_alloc(h, &h->d_err, cap * IMG_PIXELS))) return bail(rc);
+  if ((rc = dev_alloc(h, &h->d_ring, (size_t)2 * IMG_PIXELS))) return bail(rc);
+  if ((e = cudaMallocHost((void**)&h->h_img, IMG_PIXELS)) != cudaSuccess ||
+      (e = cudaMallocHost((void**)&h->h_out, (72 + IMG_PIXELS) * sizeof(float))) != cudaSuccess) {
+    h->fail(UAHN_ERR_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e));
+    return bail(UAHN_ERR_CUDA);
+  }
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) {
+    h->fail(UAHN_ERR_CUDA, "setup: %s", cudaGetErrorString(e));
+    return bail(UAHN_ERR_CUDA);
+  }
+  *out = h;
+  return UAHN_OK;
+}
+
+void uahn_destroy(uahn_handle* h) {
+  if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_img) cudaFreeHost(h->h_img);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* uahn_last_error(const uahn_handle* h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+int uahn_synchronize(uahn_handle* h) {
+  if (!h) return UAHN_ERR_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  return UAHN_OK;
+}
+void* uahn_stream(uahn_handle* h) { return h ? (void*)h->stream : nullptr; }
+uint64_t uahn_launch_count(const uahn_handle* h) { return h ? h->launches : 0; }
+double uahn_latest_inference_time(const uahn_handle* h) { return h ? h->latest_time : -1.0; }
+int uahn_image_count(const uahn_handle* h) { return h ? h->img_counter : 0; }
+
+int uahn_infer_batch_device(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior,
+                            const uahn_rng* rng, float* mean, float* cov, float* err) {
+  if (!h) return UAHN_ERR_INVALID;
+  if (!prev || !curr || !mean || !cov) return h->fail(UAHN_ERR_INVALID, "null buffer");
+  CK(cudaSetDevice(h->cfg.device));
+  return forward_any(h, n, prev, curr, prior, rng, rng ? rng->keep_masks : nullptr, mean, cov, err);
+}
+
+int uahn_infer_batch(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior,
+                     const uahn_rng* rng, float* mean, float* cov, float* err) {
+  if (!h) return UAHN_ERR_INVALID;
+  if (!prev || !curr || !mean || !cov) return h->fail(UAHN_ERR_INVALID, "null buffer");
+  if (n <= 0 || n > h->cap) return h->fail(UAHN_ERR_INVALID, "n=%d outside [1, max_batch=%d]", n, h->cap);
+  if (err && !h->cfg.show_error) return h->fail(UAHN_ERR_INVALID, "err requested but handle created with show_error=0");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(h->d_prev, prev, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_curr, curr, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, st));
+  if (prior) CK(cudaMemcpyAsync(h->d_prior, prior, (size_t)n * 8 * 4, cudaMemcpyHostToDevice, st));
+  const uint8_t* dm = nullptr;
+  if (rng && rng->keep_masks) {
+    if (!h->d_masks) {
+      int rc = dev_alloc(h, &h->d_masks, (size_t)h->cap * UAHN_MASK_BYTES_PER_PAIR, false);
+      if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(h->d_masks, rng->keep_masks, (size_t)n * UAHN_MASK_BYTES_PER_PAIR, cudaMemcpyHostToDevice, st));
+    dm = h->d_masks;
+  }
+  int rc = forward_any(h, n, h->d_prev, h->d_curr, prior ? h->d_prior : nullptr, rng, dm, h->d_mean, h->d_cov,
+                       err ? h->d_err : nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(mean, h->d_mean, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(cov, h->d_cov, (size_t)n * 64 * 4, cudaMemcpyDeviceToHost, st));
+  if (err) CK(cudaMemcpyAsync(err, h->d_err, (size_t)n * IMG_PIXELS * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return UAHN_OK;
+}
+
+int uahn_load_image(uahn_handle* h, const uint8_t* gray, int rows, int cols, size_t stride, double time_stamp) {
+  if (!h) return UAHN_ERR_INVALID;
+  if (!gray || rows != IMG_H || cols != IMG_W || stride < (size_t)IMG_W)
+    return h->fail(UAHN_ERR_INVALID, "image must be CV_8UC1 %dx%d (got %dx%d, stride %zu)", IMG_H, IMG_W, rows, cols, stride);
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));   // h_img may still be in flight from the previous frame
+  for (int y = 0; y < IMG_H; ++y) memcpy(h->h_img + (size_t)y * IMG_W, gray + (size_t)y * stride, IMG_W);
+  h->img_counter++;
+  // prev <- curr is a slot flip, not a copy (HomographyNet.cpp:143 clones the tensor)
+  h->ring_curr ^= 1;
+  CK(cudaMemcpyAsync(h->d_ring + (size_t)h->ring_curr * IMG_PIXELS, h->h_img, IMG_PIXELS, cudaMemcpyHostToDevice, h->stream));
+  if (h->img_counter >= 2) h->latest_time = time_stamp;   // HomographyNet.cpp:148
+  return UAHN_OK;
+}
+
+int uahn_infer(uahn_handle* h, const double* prior_px, const uahn_rng* rng, double* mean8, double* cov64,
+               uint8_t* err_map) {
+  if (!h) return UAHN_ERR_INVALID;
+  if (h->img_counter < 2) return h->fail(UAHN_ERR_STATE, "HNet cannot inference! Only has one image!");
+  if (!mean8 || !cov64) return h->fail(UAHN_ERR_INVALID, "null output");
+  if (err_map && !h->cfg.show_error) return h->fail(UAHN_ERR_INVALID, "err_map requested but show_error=0");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  const bool need_prior = h->cfg.variant != UAHN_VARIANT_FULL;
+  if (need_prior) {
+    if (!prior_px) return h->fail(UAHN_ERR_INVALID, "this variant needs a prior");
+    float pf[8];
+    for (int i = 0; i < 8; ++i) pf[i] = (float)prior_px[i];                 // HomographyNet.cpp:160-165 (.toType(kFloat))
+    CK(cudaMemcpyAsync(h->d_prior, pf, sizeof(pf), cudaMemcpyHostToDevice, st));   // pageable: staged before return
+  }
+  const uint8_t* dm = nullptr;
+  if (rng && rng->keep_masks) {
+    if (!h->d_masks) {
+      int rc = dev_alloc(h, &h->d_masks, (size_t)h->cap * UAHN_MASK_BYTES_PER_PAIR, false);
+      if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(h->d_masks, rng->keep_masks, UAHN_MASK_BYTES_PER_PAIR, cudaMemcpyHostToDevice, st));
+    dm = h->d_masks;
+  }
+  const uint8_t* curr = h->d_ring + (size_t)h->ring_curr * IMG_PIXELS;
+  const uint8_t* prev = h->d_ring + (size_t)(h->ring_curr ^ 1) * IMG_PIXELS;
+  int rc = forward_any(h, 1, prev, curr, need_prior ? h->d_prior : nullptr, rng, dm, h->d_mean, h->d_cov,
+                       err_map ? h->d_err : nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_out, h->d_mean, 8 * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->h_out + 8, h->d_cov, 64 * 4, cudaMemcpyDeviceToHost, st));
+  if (err_map) CK(cudaMemcpyAsync(h->h_out + 72, h->d_err, (size_t)IMG_PIXELS * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int i = 0; i < 8; ++i) mean8[i] = h->h_out[i];
+  for (int i = 0; i < 64; ++i) cov64[i] = h->h_out[8 + i];
+  if (err_map)
+    for (int i = 0; i < IMG_PIXELS; ++i) {   // .clamp(0,255).to(kU8)  (HomographyNet.cpp:201)
+      float v = h->h_out[72 + i];
+      v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
+      err_map[i] = (uint8_t)v;
+    }
+  return UAHN_OK;
+}
+
+int uahn_philox_keep_masks(uint64_t seed, uint64_t pair_index, uint8_t* out) {
+  if (!out) return UAHN_ERR_INVALID;
+  for (int head = 0; head < 2; ++head)
+    for (int s = 0; s < MC; ++s) {
+      uint8_t* row = out + ((size_t)head * MC + s) * MASK_ROW;
+      for (int k8 = 0; k8 < FC_IN / 8; ++k8) {
+        const uint32_t bits = philox_keep8(seed, pair_index, head, 0, s, k8);
+        for (int j = 0; j < 8; ++j) {
+          const int kp = k8 * 8 + j, hw = kp >> 8, c = kp & 255;   // kernel order -> reference order
+          row[c * 20 + hw] = (bits >> j) & 1u;
+        }
+      }
+      for (int j8 = 0; j8 < FC_HID / 8; ++j8) {
+        const uint32_t bits = philox_keep8(seed, pair_index, head, 1, s, j8);
+        for (int j = 0; j < 8; ++j) row[FC_IN + j8 * 8 + j] = (bits >> j) & 1u;
+      }
+    }
+  return UAHN_OK;
+}
+
+int uahn_stage_dlt(uahn_handle* h, int n, const float* offsets, float* Hout) {
+  if (!h || !offsets || !Hout) return UAHN_ERR_INVALID;
+  if (n <= 0 || n > h->cap) return h->fail(UAHN_ERR_INVALID, "n outside [1, max_batch]");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(h->d_prior, offsets, (size_t)n * 32, cudaMemcpyHostToDevice, h->stream));
+  LAUNCH(launch_dlt(n, h->d_prior, nullptr, h->Hb[0], h->stream));
+  CK(cudaMemcpyAsync(Hout, h->Hb[0], (size_t)n * 36, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return UAHN_OK;
+}
+
+int uahn_stage_warp(uahn_handle* h, int n, const uint8_t* img, const float* Hm, float* out, int16_t* ix_nw,
+                    int16_t* iy_nw) {
+  if (!h || !img || !Hm || !out) return UAHN_ERR_INVALID;
+  if (n <= 0 || n > h->cap) return h->fail(UAHN_ERR_INVALID, "n outside [1, max_batch]");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  float* d_out = nullptr;
+  int16_t *d_ix = nullptr, *d_iy = nullptr;
+  CK(cudaMalloc(&d_out, (size_t)n * IMG_PIXELS * 4));
+  CK(cudaMalloc(&d_ix, (size_t)n * IMG_PIXELS * 2));
+  CK(cudaMalloc(&d_iy, (size_t)n * IMG_PIXELS * 2));
+  CK(cudaMemcpyAsync(h->d_curr, img, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->Hb[0], Hm, (size_t)n * 36, cudaMemcpyHostToDevice, st));
+  LAUNCH(launch_warp_plain(h->d_curr, h->d_curr, h->Hb[0], d_out, d_ix, d_iy, 0, n, st));
+  CK(cudaMemcpyAsync(out, d_out, (size_t)n * IMG_PIXELS * 4, cudaMemcpyDeviceToHost, st));
+  if (ix_nw) CK(cudaMemcpyAsync(ix_nw, d_ix, (size_t)n * IMG_PIXELS * 2, cudaMemcpyDeviceToHost, st));
+  if (iy_nw) CK(cudaMemcpyAsync(iy_nw, d_iy, (size_t)n * IMG_PIXELS * 2, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d_out); cudaFree(d_ix); cudaFree(d_iy);
+  return UAHN_OK;
+}
+
+long uahn_debug_read(uahn_handle* h, const char* what, float* out, size_t capacity) {
+  if (!h || !what || !out) return UAHN_ERR_INVALID;
+  const int n = h->last_n;
+  if (n <= 0) return h->fail(UAHN_ERR_STATE, "no batch has been run");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  const std::string w(what);
+  auto copy_f32 = [&](const float* d, size_t count) -> long {
+    if (count > capacity) return h->fail(UAHN_ERR_INVALID, "capacity too small (%zu needed)", count);
+    if (cudaMemcpy(out, d, count * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return h->fail(UAHN_ERR_CUDA, "memcpy");
+    return (long)count;
+  };
+  if (w.size() == 2 && w[0] == 'H' && w[1] >= '0' && w[1] <= '3') return copy_f32(h->Hb[w[1] - '0'], (size_t)n * 9);
+  if (w == "Htot") return copy_f32(h->Htot, (size_t)n * 9);
+  if (w.size() == 2 && w[0] == 'd' && w[1] >= '1' && w[1] <= '3') return copy_f32(h->dblk[w[1] - '0'], (size_t)n * 8);
+  if (w == "mcmean") return copy_f32(h->mc_mean, (size_t)n * MC * 8);
+  if (w == "mclogvar") return copy_f32(h->mc_logvar, (size_t)n * MC * 8);
+  // tensors stored in the activation dtype: "feat<b>", "x<b>", "act:<layer name>"
+  const Tensor* t = nullptr;
+  bool nchw_flat = false;
+  if (w.rfind("feat", 0) == 0 && w.size() == 5) {
+    const int b = w[4] - '0';
+    if (b < 1 || b > 4 || !h->blocks[b].active) return h->fail(UAHN_ERR_INVALID, "block not active");
+    t = &h->blocks[b].layers.back().out;
+    nchw_flat = true;
+  } else if (w.rfind("x", 0) == 0 && w.size() == 2) {
+    const int b = w[1] - '0';
+    if (b < 1 || b > 4 || !h->blocks[b].active) return h->fail(UAHN_ERR_INVALID, "block not active");
+    t = &h->blocks[b].x;
+  } else if (w.rfind("act:", 0) == 0) {
+    for (int b = 1; b <= 4 && !t; ++b)
+      for (auto& L : h->blocks[b].layers)
+        if (h->blocks[b].active && w.substr(4) == L.spec.name) t = &L.out;
+  }
+  if (!t) return h->fail(UAHN_ERR_INVALID, "unknown debug tensor '%s'", what);
+  const size_t count = (size_t)n * t->C * t->H * t->W;
+  if (count > capacity) return h->fail(UAHN_ERR_INVALID, "capacity too small (%zu needed)", count);
+  std::vector<uint8_t> raw((size_t)n * t->pitch_n * h->es);
+  if (cudaMemcpy(raw.data(), t->p, raw.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return h->fail(UAHN_ERR_CUDA, "memcpy");
+  (void)nchw_flat;   // all activation reads are returned NCHW: [n][C][H][W]
+  for (int i = 0; i < n; ++i)
+    for (int c = 0; c < t->C; ++c)
+      for (int y = 0; y < t->H; ++y)
+        for (int x = 0; x < t->W; ++x) {
+          const size_t src = (size_t)t->off(i, y, x, c);
+          float v;
+          if (h->bf16) {
+            uint32_t bits = (uint32_t)reinterpret_cast<const uint16_t*>(raw.data())[src] << 16;
+            memcpy(&v, &bits, 4);
+          } else {
+            v = reinterpret_cast<const float*>(raw.data())[src];
+          }
+          out[(((size_t)i * t->C + c) * t->H + y) * t->W + x] = v;
+        }
+  return (long)count;
+}
+
+}  // extern "C"

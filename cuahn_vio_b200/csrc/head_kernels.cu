@@ -1,0 +1,387 @@
+// Regression / uncertainty head kernels of the UAHN cascade:
+//   * 4-point DLT solve (model_to_trace.py:42-61): one warp per pair, Gauss-Jordan with partial pivoting,
+//     rows held one-per-lane, pivot search and row broadcast by warp shuffles, fp64 accumulation
+//   * Linear(5120->8) + DLT + homography composition H <- H·H_b (model_to_trace.py:143-150,163-168,183-188)
+//   * MC-dropout expansion of the block-4 feature (model_to_trace.py:222-235,272-273)
+//   * second head layer, 16-sample ensemble (model_to_trace.py:274-281), covariance transfer
+//     (model_to_trace.py:18-38), output packing and the showError homography (model_to_trace.py:311-323)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace uahn {
+namespace {
+
+__device__ __forceinline__ void corner(int i, float& x, float& y) {   // model_to_trace.py:78-83: UL, BL, BR, UR
+  x = (i == 2 || i == 3) ? (float)(IMG_W - 1) : 0.f;
+  y = (i == 1 || i == 2) ? (float)(IMG_H - 1) : 0.f;
+}
+
+// All 32 lanes call with the same `dst` (4 destination points, fp32 like the reference's `pts0 + d`).
+// Lane r (mod 8) owns row r of the 8x9 augmented system; result h[0..8] (h[8] = 1) on every lane.
+__device__ void dlt_warp(const float* dst, double* h) {
+  const int lane = threadIdx.x & 31, r = lane & 7, pt = r >> 1;
+  float sx, sy;
+  corner(pt, sx, sy);
+  const double x = sx, y = sy, u = dst[2 * pt], v = dst[2 * pt + 1];
+  double a[9];
+  if ((r & 1) == 0) {
+    a[0] = x; a[1] = y; a[2] = 1; a[3] = 0; a[4] = 0; a[5] = 0; a[6] = -u * x; a[7] = -u * y; a[8] = u;
+  } else {
+    a[0] = 0; a[1] = 0; a[2] = 0; a[3] = x; a[4] = y; a[5] = 1; a[6] = -v * x; a[7] = -v * y; a[8] = v;
+  }
+  bool used = false;
+  int mycol = -1;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    double best = used ? -1.0 : fabs(a[c]);
+    int bi = r;
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, off, 8);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off, 8);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    const int p = bi;
+    const double piv = __shfl_sync(0xffffffffu, a[c], p, 8);
+    const double f = a[c] / piv;
+#pragma unroll
+    for (int j = c; j < 9; ++j) {
+      const double pj = __shfl_sync(0xffffffffu, a[j], p, 8);
+      if (r != p) a[j] -= f * pj;
+    }
+    if (r == p) { used = true; mycol = c; }
+  }
+  double diag = 1.0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (mycol == c) diag = a[c];
+  const double xr = a[8] / diag;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const unsigned m = __ballot_sync(0xffffffffu, mycol == c && lane < 8);
+    const int owner = m ? (__ffs(m) - 1) : 0;
+    h[c] = __shfl_sync(0xffffffffu, xr, owner);
+  }
+  h[8] = 1.0;
+}
+
+// fp32 3x3 product, k accumulated sequentially with FMA (torch.bmm on CPU)
+__device__ __forceinline__ void mat3_mul(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      C[i * 3 + j] = __fmaf_rn(A[i * 3 + 2], B[6 + j], __fmaf_rn(A[i * 3 + 1], B[3 + j], __fmul_rn(A[i * 3], B[j])));
+}
+
+// H = DLT(pts0, pts0 + off); optional left-multiplication by Hprev.  One warp per pair.
+__global__ void dlt_kernel(int n, const float* __restrict__ off, const float* __restrict__ Hprev, float* __restrict__ Hout) {
+  const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (pair >= n) return;
+  float dst[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float x, y;
+    corner(i, x, y);
+    dst[2 * i] = __fadd_rn(x, off[pair * 8 + 2 * i]);
+    dst[2 * i + 1] = __fadd_rn(y, off[pair * 8 + 2 * i + 1]);
+  }
+  double h[9];
+  dlt_warp(dst, h);
+  if ((threadIdx.x & 31) == 0) {
+    float hb[9], out[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) hb[i] = (float)h[i];
+    if (Hprev) {
+      float hp[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) hp[i] = Hprev[pair * 9 + i];
+      mat3_mul(hp, hb, out);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) out[i] = hb[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Hout[pair * 9 + i] = out[i];
+  }
+}
+
+// d = W8·feat + b8 ; H_b = DLT(pts0, pts0 + d) ; Hout = Hprev ? Hprev·H_b : H_b.   One CTA per pair.
+// feat is the last conv output in NHWC order ((h*5+w)*256 + c); W8 was permuted to that order at load.
+template <typename T>
+__global__ void __launch_bounds__(256) fc8_dlt_kernel(const T* __restrict__ feat, const float* __restrict__ W8,
+                                                       const float* __restrict__ b8, const float* __restrict__ Hprev,
+                                                       float* __restrict__ Hout, float* __restrict__ dout) {
+  __shared__ float part[8][8];
+  __shared__ float d_s[8];
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const T* f = feat + (size_t)pair * FC_IN;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+  for (int k = tid; k < FC_IN; k += 256) {
+    const float x = to_f32<T>(f[k]);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = fmaf(x, __ldg(W8 + o * FC_IN + k), acc[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+    if (lane == 0) part[wid][o] = acc[o];
+  }
+  __syncthreads();
+  if (tid < 8) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w][tid];
+    s += b8[tid];
+    d_s[tid] = s;
+    if (dout) dout[pair * 8 + tid] = s;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    float dst[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x, y;
+      corner(i, x, y);
+      dst[2 * i] = __fadd_rn(x, d_s[2 * i]);
+      dst[2 * i + 1] = __fadd_rn(y, d_s[2 * i + 1]);
+    }
+    double h[9];
+    dlt_warp(dst, h);
+    if (lane == 0) {
+      float hb[9], out[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) hb[i] = (float)h[i];
+      if (Hprev) {
+        float hp[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) hp[i] = Hprev[pair * 9 + i];
+        mat3_mul(hp, hb, out);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) out[i] = hb[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Hout[pair * 9 + i] = out[i];
+    }
+  }
+}
+
+// A'[head][pair][s][k'] = keep ? feat[k'] * (1/0.95) : 0     (Dropout(0.05) on the repeated feature)
+// k' = NHWC index (hw*256 + c); explicit masks are indexed in the reference order kref = c*20 + hw.
+template <typename T>
+__global__ void __launch_bounds__(256) mc_expand_kernel(const T* __restrict__ feat, T* __restrict__ A, int n,
+                                                         const uint8_t* __restrict__ keep_masks, uint64_t seed,
+                                                         uint64_t first_pair) {
+  const int pair = blockIdx.x, head = blockIdx.y;
+  const T* f = feat + (size_t)pair * FC_IN;
+  T* a = A + ((size_t)head * n + pair) * MC * FC_IN;
+  for (int i = threadIdx.x; i < MC * (FC_IN / 8); i += blockDim.x) {
+    const int s = i / (FC_IN / 8), k8 = i - s * (FC_IN / 8);
+    uint32_t bits;
+    if (keep_masks) {
+      const uint8_t* m = keep_masks + ((size_t)(pair * 2 + head) * MC + s) * MASK_ROW;
+      bits = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kp = k8 * 8 + j, hw = kp >> 8, c = kp & 255;
+        bits |= (m[c * 20 + hw] ? 1u : 0u) << j;
+      }
+    } else {
+      bits = philox_keep8(seed, first_pair + pair, head, 0, s, k8);
+    }
+    T v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = to_f32<T>(f[k8 * 8 + j]);
+      v[j] = from_f32<T>((bits >> j) & 1u ? __fmul_rn(x, KEEP_SCALE) : 0.f);
+    }
+    T* dstp = a + (size_t)s * FC_IN + k8 * 8;
+    if constexpr (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(dstp) = *reinterpret_cast<const uint4*>(v);
+    } else {
+      *reinterpret_cast<float4*>(dstp) = *reinterpret_cast<const float4*>(v);
+      *reinterpret_cast<float4*>(dstp + 4) = *reinterpret_cast<const float4*>(v + 4);
+    }
+  }
+}
+
+struct HeadOut {
+  float* mean;     // [n][8]
+  float* cov;      // [n][64]
+  float* Htot;     // [n][9] or null (showError)
+  float* mc_mean;  // [n][16][8] or null (debug tap)
+  float* mc_logvar;
+};
+
+// hid: [head][pair][s][256] = LeakyReLU(Linear(5120->256)(dropped feature)).  One CTA (256 threads) per pair:
+// thread (head, s, o) does the second dropout + Linear(256->8); then ensemble, transfer, packing.
+template <typename T>
+__global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid, int n, const float* __restrict__ W2m,
+                                                        const float* __restrict__ b2m, const float* __restrict__ W2u,
+                                                        const float* __restrict__ b2u, const float* __restrict__ Hpart1,
+                                                        const uint8_t* __restrict__ keep_masks, uint64_t seed,
+                                                        uint64_t first_pair, HeadOut o) {
+  __shared__ float w2[2][8][FC_HID];
+  __shared__ float outv[2][MC][8];
+  __shared__ float mu_s[8], var_s[8];
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < 8 * FC_HID; i += 256) {
+    w2[0][i / FC_HID][i % FC_HID] = W2m[i];
+    w2[1][i / FC_HID][i % FC_HID] = W2u[i];
+  }
+  __syncthreads();
+  {
+    const int head = tid >> 7, s = (tid >> 3) & 15, oo = tid & 7;
+    const T* hrow = hid + (((size_t)head * n + pair) * MC + s) * FC_HID;
+    const uint8_t* m = keep_masks ? keep_masks + ((size_t)(pair * 2 + head) * MC + s) * MASK_ROW + FC_IN : nullptr;
+    float acc = 0.f;
+    for (int j8 = 0; j8 < FC_HID / 8; ++j8) {
+      uint32_t bits;
+      if (m) {
+        bits = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bits |= (m[j8 * 8 + j] ? 1u : 0u) << j;
+      } else {
+        bits = philox_keep8(seed, first_pair + pair, head, 1, s, j8);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float hv = to_f32<T>(hrow[j8 * 8 + j]);
+        const float x = (bits >> j) & 1u ? __fmul_rn(hv, KEEP_SCALE) : 0.f;
+        acc = fmaf(x, w2[head][oo][j8 * 8 + j], acc);
+      }
+    }
+    acc += head ? b2u[oo] : b2m[oo];
+    if (head) acc = __fmul_rn(acc, 1e-03f);      // model_to_trace.py:256
+    outv[head][s][oo] = acc;
+    if (o.mc_mean && !head) o.mc_mean[((size_t)pair * MC + s) * 8 + oo] = acc;
+    if (o.mc_logvar && head) o.mc_logvar[((size_t)pair * MC + s) * 8 + oo] = acc;
+  }
+  __syncthreads();
+  if (tid < 8) {                                 // model_to_trace.py:274-280
+    float sm = 0.f, sv = 0.f;
+#pragma unroll
+    for (int s = 0; s < MC; ++s) {
+      sm += outv[0][s][tid];
+      sv += expf(outv[1][s][tid]);
+    }
+    const float mu = sm / (float)MC, avg_pred = sv / (float)MC;
+    float se = 0.f;
+#pragma unroll
+    for (int s = 0; s < MC; ++s) {
+      const float d = mu - outv[0][s][tid];
+      se += d * d;
+    }
+    mu_s[tid] = mu;
+    var_s[tid] = se / (float)MC + avg_pred;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int lane = tid;
+    float Hp[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Hp[i] = Hpart1[pair * 9 + i];
+    float ptsw[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x, y;
+      corner(i, x, y);
+      ptsw[2 * i] = __fadd_rn(x, mu_s[2 * i]);          // model_to_trace.py:281
+      ptsw[2 * i + 1] = __fadd_rn(y, mu_s[2 * i + 1]);
+    }
+    if (lane < 4) {                                     // transfer_mean_var_single, one point per lane
+      const int i = lane;
+      const float u = ptsw[2 * i], v = ptsw[2 * i + 1];
+      float p[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        p[r] = __fmaf_rn(Hp[r * 3 + 2], 1.f, __fmaf_rn(Hp[r * 3 + 1], v, __fmul_rn(Hp[r * 3], u)));
+      const float sc = p[2];
+      float x0, y0;
+      corner(i, x0, y0);
+      o.mean[pair * 8 + 2 * i] = __fsub_rn(__fdiv_rn(p[0], sc), x0);          // model_to_trace.py:311
+      o.mean[pair * 8 + 2 * i + 1] = __fsub_rn(__fdiv_rn(p[1], sc), y0);
+      float Hs[9];
+#pragma unroll
+      for (int r = 0; r < 9; ++r) Hs[r] = __fdiv_rn(Hp[r], sc);               // model_to_trace.py:30
+      const float vu = var_s[2 * i], vv = var_s[2 * i + 1];
+      float c2[2][2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const float t0 = __fmul_rn(Hs[a * 3], vu), t1 = __fmul_rn(Hs[a * 3 + 1], vv);
+          c2[a][b] = __fmaf_rn(t1, Hs[b * 3 + 1], __fmul_rn(t0, Hs[b * 3]));   // third term is exactly 0
+        }
+      float* cv = o.cov + (size_t)pair * 64;
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) cv[(2 * i + a) * 8 + b] = (b >> 1) == i ? c2[a][b & 1] : 0.f;
+    }
+    if (o.Htot) {                                       // model_to_trace.py:321-323
+      double h4[9];
+      dlt_warp(ptsw, h4);
+      if (lane == 0) {
+        float hb[9], out[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) hb[i] = (float)h4[i];
+        mat3_mul(Hp, hb, out);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o.Htot[pair * 9 + i] = out[i];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_dlt(int n, const float* off, const float* Hprev, float* Hout, cudaStream_t st) {
+  const int threads = 128, pairs_per_block = threads / 32;
+  dlt_kernel<<<(n + pairs_per_block - 1) / pairs_per_block, threads, 0, st>>>(n, off, Hprev, Hout);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_fc8_dlt(int n, const T* feat, const float* W8, const float* b8, const float* Hprev, float* Hout,
+                           float* dout, cudaStream_t st) {
+  fc8_dlt_kernel<T><<<n, 256, 0, st>>>(feat, W8, b8, Hprev, Hout, dout);
+  return cudaGetLastError();
+}
+template cudaError_t launch_fc8_dlt<float>(int, const float*, const float*, const float*, const float*, float*, float*,
+                                           cudaStream_t);
+template cudaError_t launch_fc8_dlt<__nv_bfloat16>(int, const __nv_bfloat16*, const float*, const float*, const float*,
+                                                   float*, float*, cudaStream_t);
+
+template <typename T>
+cudaError_t launch_mc_expand(int n, const T* feat, T* A, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,
+                             cudaStream_t st) {
+  mc_expand_kernel<T><<<dim3(n, 2), 256, 0, st>>>(feat, A, n, keep_masks, seed, first_pair);
+  return cudaGetLastError();
+}
+template cudaError_t launch_mc_expand<float>(int, const float*, float*, const uint8_t*, uint64_t, uint64_t,
+                                             cudaStream_t);
+template cudaError_t launch_mc_expand<__nv_bfloat16>(int, const __nv_bfloat16*, __nv_bfloat16*, const uint8_t*,
+                                                     uint64_t, uint64_t, cudaStream_t);
+
+template <typename T>
+cudaError_t launch_mc_final(int n, const T* hid, const float* W2m, const float* b2m, const float* W2u,
+                            const float* b2u, const float* Hpart1, const uint8_t* keep_masks, uint64_t seed,
+                            uint64_t first_pair, float* mean, float* cov, float* Htot, float* mc_mean,
+                            float* mc_logvar, cudaStream_t st) {
+  HeadOut o{mean, cov, Htot, mc_mean, mc_logvar};
+  mc_final_kernel<T><<<n, 256, 0, st>>>(hid, n, W2m, b2m, W2u, b2u, Hpart1, keep_masks, seed, first_pair, o);
+  return cudaGetLastError();
+}
+template cudaError_t launch_mc_final<float>(int, const float*, const float*, const float*, const float*, const float*,
+                                            const float*, const uint8_t*, uint64_t, uint64_t, float*, float*, float*,
+                                            float*, float*, cudaStream_t);
+template cudaError_t launch_mc_final<__nv_bfloat16>(int, const __nv_bfloat16*, const float*, const float*,
+                                                    const float*, const float*, const float*, const uint8_t*, uint64_t,
+                                                    uint64_t, float*, float*, float*, float*, float*, cudaStream_t);
+
+}  // namespace uahn

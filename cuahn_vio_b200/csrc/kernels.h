@@ -1,0 +1,32 @@
+// Launch wrappers of the UAHN kernels (definitions in the .cu files next to this header).
+#pragma once
+#include "common.cuh"
+
+namespace uahn {
+
+// image_kernels.cu
+template <typename T>
+cudaError_t launch_warp_concat_pool(const uint8_t* prev, const uint8_t* curr, const float* Hmat, const Tensor& out,
+                                    int pool, int n, cudaStream_t st);
+cudaError_t launch_warp_plain(const uint8_t* prev, const uint8_t* curr, const float* Hmat, float* out, int16_t* ix,
+                              int16_t* iy, int error_map, int n, cudaStream_t st);
+
+// conv_f32.cu
+cudaError_t launch_conv_f32(const float* in, const float* wk, const float* bias, float* out, const ConvGeom& g,
+                            cudaStream_t st);
+
+// head_kernels.cu
+cudaError_t launch_dlt(int n, const float* off, const float* Hprev, float* Hout, cudaStream_t st);
+template <typename T>
+cudaError_t launch_fc8_dlt(int n, const T* feat, const float* W8, const float* b8, const float* Hprev, float* Hout,
+                           float* dout, cudaStream_t st);
+template <typename T>
+cudaError_t launch_mc_expand(int n, const T* feat, T* A, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,
+                             cudaStream_t st);
+template <typename T>
+cudaError_t launch_mc_final(int n, const T* hid, const float* W2m, const float* b2m, const float* W2u,
+                            const float* b2u, const float* Hpart1, const uint8_t* keep_masks, uint64_t seed,
+                            uint64_t first_pair, float* mean, float* cov, float* Htot, float* mc_mean,
+                            float* mc_logvar, cudaStream_t st);
+
+}  // namespace uahn

@@ -1,0 +1,210 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the oracle / the fixtures recorded from the reference.
+
+Tolerances (BASELINE.json north_star): fp32 mode — corner offsets within 1e-3 px, warp sampling indices
+bit-exact; bf16 mode — offsets within 0.05 px, covariance within 1 % relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import unpack_masks
+from cuahn_vio_b200 import synthetic as S
+from oracle import uahn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_PX = 1e-3
+BF16_PX = 0.05
+BF16_COV_REL = 0.01
+
+
+@pytest.fixture(scope="module")
+def wfile():
+    from cuahn_vio_b200 import build, weights
+    build.build()
+    return weights.synthetic_weights_file(0)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from cuahn_vio_b200 import api
+    return api
+
+
+def _masks_for(n, seed0=20240 + 10 ** 6):
+    return [S.torch_dropout_masks(seed0 + i) for i in range(n)]
+
+
+def _pack(api, masks_list):
+    return np.stack([api.pack_keep_masks(m) for m in masks_list])
+
+
+def _oracle_batch(prev, curr, sd, masks_list, priors, show_error, btr=3):
+    return O.forward_batch(prev, curr, sd, masks_list, priors, show_error, btr)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_stage_dlt_matches_reference(api, wfile, golden_stages):
+    g = golden_stages
+    with api.Uahn(wfile, "prior1", max_batch=64) as net:
+        Hg = net.stage_dlt(g["dlt_offsets"].reshape(-1, 8))
+        assert np.abs(Hg - g["dlt_H"]).max() < 2e-4           # fp32 torch.inverse noise (cond ~1.8e5)
+        assert np.abs(Hg[0] - np.eye(3)).max() < 1e-6         # DLT(p, p) = I
+        rng = np.random.default_rng(3)
+        off = ((rng.random((64, 4, 2)) * 2 - 1) * 30).astype(np.float32)
+        Hd = net.stage_dlt(off.reshape(-1, 8))
+        pts0 = O.origin_4pt().unsqueeze(0).double()
+        for i in range(64):
+            # fp64 torch reference of the same solve: the kernel accumulates in fp64
+            Hr = O.dlt_solve(pts0, pts0 + torch.from_numpy(off[i:i + 1]).double())[0].numpy()
+            assert np.abs(Hd[i] - Hr).max() / max(1.0, np.abs(Hr).max()) < 1e-6
+            # and it must map the corners onto corners + offsets
+            p = Hd[i].astype(np.float64) @ np.concatenate([S.ORIGIN_4PT.T, np.ones((1, 4))])
+            assert np.abs((p[:2] / p[2]).T - (S.ORIGIN_4PT + off[i])).max() < 2e-3
+
+
+def test_stage_warp_indices_bit_exact(api, wfile, golden_stages):
+    g = golden_stages
+    with api.Uahn(wfile, "prior1", max_batch=8) as net:
+        img = np.repeat(g["warp_src_u8"][None], 4, 0)
+        out, ix, iy = net.stage_warp(img, g["warp_H"])
+        assert np.array_equal(ix, g["warp_ix"]) and np.array_equal(iy, g["warp_iy"])   # fixtures from the reference
+        assert np.abs(out - g["warp_out"]).max() < 2e-6
+        # random homographies incl. large ones that leave the image; oracle computed here
+        rng = np.random.default_rng(11)
+        Hs = []
+        for t in range(8):
+            disp = (rng.random((4, 2)) * 2 - 1) * (20 if t < 6 else 150)
+            Hs.append(S.dlt_numpy(S.ORIGIN_4PT.astype(np.float64), S.ORIGIN_4PT + disp).astype(np.float32))
+        Hs = np.stack(Hs)
+        img8 = np.repeat(g["warp_src_u8"][None], 8, 0)
+        out, ix, iy = net.stage_warp(img8, Hs)
+        src = O.u8_to_unit(g["warp_src_u8"])
+        mism = 0
+        for t in range(8):
+            Ht = torch.from_numpy(Hs[t])
+            rix, riy, _, _ = O.sample_indices(Ht)
+            inside = (rix.numpy() >= -1) & (rix.numpy() <= 320) & (riy.numpy() >= -1) & (riy.numpy() <= 224)
+            mism += int((ix[t][inside] != rix.numpy()[inside]).sum() + (iy[t][inside] != riy.numpy()[inside]).sum())
+            assert np.abs(out[t] - O.warp_image(src, Ht)[0, 0].numpy()).max() < 2e-6
+        assert mism == 0
+
+
+def test_warp_identity_and_outside(api, wfile):
+    with api.Uahn(wfile, "prior1", max_batch=2) as net:
+        rng = np.random.default_rng(0)
+        img = rng.integers(0, 256, (2, 224, 320), dtype=np.uint8)
+        far = np.eye(3, dtype=np.float32); far[0, 2] = 1000.0
+        out, _, _ = net.stage_warp(img, np.stack([np.eye(3, dtype=np.float32), far]))
+        assert np.abs(out[0] - img[0].astype(np.float32) / np.float32(255)).max() < 1e-4
+        assert np.abs(out[1]).max() == 0.0
+
+
+@pytest.mark.parametrize("variant,show", [("prior3", True), ("full", True), ("prior2", False), ("prior1", False)])
+def test_e2e_fp32_vs_oracle(api, wfile, synth_sd, variant, show):
+    n = 4
+    prev, curr, gt, prior = S.synthetic_batch(n, start=100)
+    masks = _masks_for(n)
+    btr = {"prior3": 3, "prior2": 2, "prior1": 1, "full": 3}[variant]
+    pr = None if variant == "full" else prior
+    om, oc, oe = _oracle_batch(prev, curr, synth_sd, masks, pr, show, btr)
+    with api.Uahn(wfile, variant, show_error=show, precision="fp32", max_batch=n) as net:
+        m, c, e = net.infer_batch(prev, curr, pr, keep_masks=_pack(api, masks), want_error=show)
+        assert np.abs(m - om).max() < FP32_PX, np.abs(m - om).max()
+        assert np.abs(c - oc).max() <= 2e-4 * np.abs(oc).max()
+        assert np.abs(c - np.swapaxes(c, 1, 2)).max() == 0          # symmetric (Eigen::Map reads it transposed)
+        if show:
+            assert np.abs(e - oe).max() < 0.05 and np.abs(e - oe).mean() < 1e-3   # 255-scaled grey levels
+        # stage taps vs the oracle's taps for pair 0
+        t = O.Taps()
+        O.forward(O.u8_to_unit(prev[0]), O.u8_to_unit(curr[0]), synth_sd, masks[0],
+                  None if pr is None else torch.from_numpy(pr[0]).view(1, 1, 4, 2), show, btr, taps=t)
+        for b in (1, 2, 3):
+            if b in t.d:
+                assert np.abs(net.debug_read(f"d{b}", (n, 8))[0] - t.d[b].numpy()).max() < 2e-4
+                assert np.abs(net.debug_read(f"H{b}", (n, 3, 3))[0] - t.H[b][0].numpy()).max() < 2e-4
+                assert np.abs(net.debug_read(f"x{b}", (n,) + tuple(t.x_in[b].shape[1:]))[0] - t.x_in[b][0].numpy()).max() < 2e-5
+        f4 = net.debug_read("feat4", (n, 256, 4, 5))[0]
+        ref4 = t.feat[4][0].numpy()
+        assert np.abs(f4 - ref4).max() < 1e-4 * max(1.0, np.abs(ref4).max())
+        assert np.abs(net.debug_read("mcmean", (n, 16, 8))[0] - t.mc_mean.reshape(16, 8).numpy()).max() < 2e-4
+
+
+def test_e2e_fp32_vs_reference_fixtures(api, wfile, golden_e2e):
+    g = golden_e2e
+    masks = np.stack([api.pack_keep_masks(unpack_masks(g, i)) for i in range(3)])
+    for variant in ("prior3", "full"):
+        with api.Uahn(wfile, variant, show_error=True, precision="fp32", max_batch=3) as net:
+            m, c, e = net.infer_batch(g["prev"], g["curr"], g["prior"] if variant == "prior3" else None,
+                                      keep_masks=masks, want_error=True)
+            for i in range(3):
+                assert np.abs(m[i] - g[f"flow_{variant}_{i}"]).max() < FP32_PX
+                assert np.abs(c[i] - g[f"cov_{variant}_{i}"]).max() < 2e-4 * np.abs(g[f"cov_{variant}_{i}"]).max()
+                assert abs(float(e[i].astype(np.float64).sum()) - float(g[f"errsum_{variant}_{i}"])) < 1e-4 * float(g[f"errsum_{variant}_{i}"])
+            assert np.abs(e[0] - g[f"err_{variant}_0"]).max() < 0.05
+
+
+def test_batch_equals_loop_and_is_deterministic(api, wfile):
+    n = 6
+    prev, curr, _, prior = S.synthetic_batch(n, start=300)
+    with api.Uahn(wfile, "prior3", precision="fp32", max_batch=n) as net:
+        m, c, _ = net.infer_batch(prev, curr, prior, seed=5, first_pair=40)
+        m2, c2, _ = net.infer_batch(prev, curr, prior, seed=5, first_pair=40)
+        assert np.array_equal(m, m2) and np.array_equal(c, c2)
+        for i in range(n):
+            mi, ci, _ = net.infer_batch(prev[i:i + 1], curr[i:i + 1], prior[i:i + 1], seed=5, first_pair=40 + i)
+            assert np.array_equal(mi[0], m[i]) and np.array_equal(ci[0], c[i])
+        m3, _, _ = net.infer_batch(prev, curr, prior, seed=6, first_pair=40)
+        assert not np.array_equal(m, m3)     # MC dropout really is stochastic in the seed
+
+
+def test_philox_masks_replayed_through_oracle(api, wfile, synth_sd):
+    n = 2
+    prev, curr, _, prior = S.synthetic_batch(n, start=500)
+    with api.Uahn(wfile, "prior3", precision="fp32", max_batch=n) as net:
+        m, c, _ = net.infer_batch(prev, curr, prior, seed=1234, first_pair=7)
+    masks = []
+    for i in range(n):
+        k = api.philox_keep_masks(1234, 7 + i).astype(np.float32) * np.float32(1.0 / 0.95)
+        masks.append(tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in
+                           (k[0, :, :5120], k[0, :, 5120:], k[1, :, :5120], k[1, :, 5120:])))
+    om, oc, _ = _oracle_batch(prev, curr, synth_sd, masks, prior, False)
+    assert np.abs(m - om).max() < FP32_PX and np.abs(c - oc).max() < 2e-4 * np.abs(oc).max()
+
+
+def test_streaming_call_surface(api, wfile):
+    prev, curr, _, prior = S.synthetic_batch(3, start=700)
+    frames = [prev[0], curr[0], curr[1]]
+    with api.Uahn(wfile, "prior3", show_error=True, precision="fp32", max_batch=1) as net:
+        net.load_image(frames[0], 1.0)
+        with pytest.raises(api.UahnError):           # HomographyNet.cpp:155-158
+            net.infer(prior[0].reshape(8))
+        assert net.latest_inference_time == -1.0
+        net.load_image(frames[1], 2.0)
+        assert net.img_counter == 2 and net.latest_inference_time == 2.0
+        m, c, e = net.infer(prior[0].reshape(8), seed=9, pair_index=0, want_error=True)
+        mb, cb, eb = net.infer_batch(frames[0][None], frames[1][None], prior[:1], seed=9, first_pair=0, want_error=True)
+        assert np.array_equal(m.astype(np.float32), mb[0]) and np.array_equal(c.astype(np.float32), cb[0])
+        assert np.array_equal(e, np.clip(eb[0], 0, 255).astype(np.uint8))
+        net.load_image(frames[2], 3.0)               # prev <- curr slot flip
+        m2, _, _ = net.infer(prior[1].reshape(8), seed=9, pair_index=1)
+        mb2, _, _ = net.infer_batch(frames[1][None], frames[2][None], prior[1:2], seed=9, first_pair=1)
+        assert np.array_equal(m2.astype(np.float32), mb2[0])
+    hn = api.HomographyNet(wfile, use_prior=True, precision="fp32")
+    hn.load_current_img(frames[0], 0.1)
+    hn.network_inference(prior[0].reshape(8), 0)     # prints, leaves outputs untouched
+    assert np.all(hn.get_pred_mean() == 0)
+    hn.load_current_img(frames[1], 0.2)
+    hn.network_inference(prior[0].reshape(8), 0)
+    assert np.abs(hn.get_pred_mean()).max() > 0 and hn.get_latest_inference_time() == 0.2
+
+
+def test_error_paths(api, wfile):
+    with api.Uahn(wfile, "prior3", precision="fp32", max_batch=2) as net:
+        prev, curr, _, prior = S.synthetic_batch(3, start=0)
+        with pytest.raises(api.UahnError):
+            net.infer_batch(prev, curr, prior)              # n > max_batch
+        with pytest.raises(api.UahnError):
+            net.infer_batch(prev[:1], curr[:1], None)       # prior variant without prior
+        with pytest.raises(api.UahnError):
+            net.load_image(np.zeros((100, 100), np.uint8))
