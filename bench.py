@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — UAHN image-pair inferences/sec on N B200 (BASELINE.json metric) + p50 batch-1 latency.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+A "step" is one pass of the hot path (3-block UAHN with EKF prior: prior DLT, blocks 2,3 and the
+uncertainty block 4, covariance transfer) over one batch of `--batch` synthetic textured pairs per GPU.
+N > 1 is launched by torchrun (one rank per GPU); pairs are independent, so ranks never exchange data on
+the timed path — NCCL is used only for the start/stop barrier and the max-over-ranks of the device time.
+
+Printed JSON (one line, rank 0): value = whole-job pairs/s with inputs resident in HBM; e2e = the same
+through the host-buffer C-ABI call (pinned host inputs, H2D + D2H inside the timed region); roofline =
+the conv implicit-GEMM kernels (tensor-bound) timed with CUDA events inside the timed region;
+cpu_baseline = the reference's own TorchScript graph (oracle/_ref) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "UAHN image-pair inferences/sec"
+UNIT = "pairs/s"
+# algorithmic work per pair, 3-block variant (SURVEY §8d / BASELINE.md §4)
+CONV_MACS = 463_892_480
+MC_GEMM_MACS = 2 * 16 * 5120 * 256
+TOTAL_MACS = 505_982_976
+WARP_BYTES = 573_440
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("UAHN_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=1024, help="pairs per GPU per step (8192 / 8)")
+    ap.add_argument("--chunk", type=int, default=0, help="pairs per infer_batch call (0 = whole batch)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.dev = device_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+def reference_runner(variant: str = "prior3"):
+    """Callable running ONE pair through the reference's CPU implementation + its description.
+
+    kind "reference": the TorchScript trace of the unmodified reference model (oracle/_ref, built in the
+    container by oracle/build_ref.py) executed by libtorch on the host cores.  kind "port": the oracle
+    restatement (same ATen ops) when the prebuilt trace is absent.
+    """
+    import numpy as np
+    import torch
+    from cuahn_vio_b200 import synthetic as S
+    name = {"prior3": "traced_model_3_blocks_using_prior.pt", "full": "traced_full_model.pt"}[variant]
+    path = os.path.join(ROOT, "oracle", "_ref", name)
+    prev, curr, _, prior = S.synthetic_batch(16)
+    i1 = [torch.from_numpy(p).float().div(255.0).view(1, 1, 224, 320) for p in prev]
+    i2 = [torch.from_numpy(c).float().div(255.0).view(1, 1, 224, 320) for c in curr]
+    pr = [torch.from_numpy(p).view(1, 1, 4, 2) for p in prior]
+    if os.path.exists(path):
+        mod = torch.jit.load(path, map_location="cpu")
+        mod.eval()
+
+        def run(i):
+            j = i % 16
+            with torch.no_grad():
+                return mod(i1[j], i2[j], pr[j]) if variant == "prior3" else mod(i1[j], i2[j])
+        kind = "reference"
+    else:
+        from oracle import uahn_oracle as O
+        sd = S.synthetic_state_dict(0)
+        masks = S.torch_dropout_masks(0)
+
+        def run(i):
+            j = i % 16
+            return O.forward(i1[j], i2[j], sd, masks, pr[j] if variant == "prior3" else None)
+        kind = "port"
+    return run, kind, torch.get_num_threads()
+
+
+def time_reference(seconds: float, variant: str = "prior3", max_calls: int = 4000, warm: int = 20):
+    run, kind, threads = reference_runner(variant)
+    for i in range(warm):
+        run(i)
+    lat = []
+    t_end = time.perf_counter() + seconds
+    i = 0
+    while time.perf_counter() < t_end and i < max_calls:
+        t0 = time.perf_counter()
+        run(i)
+        lat.append(time.perf_counter() - t0)
+        i += 1
+    total = sum(lat)
+    return {"value": len(lat) / total, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{len(lat)} sequential batch-1 forwards of the {variant} graph after {warm} warm-up "
+                      f"(libtorch CPU, {threads} threads, {os.cpu_count()} host cpus)",
+            "p50_ms": 1e3 * statistics.median(lat), "p90_ms": 1e3 * sorted(lat)[int(0.9 * (len(lat) - 1))]}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    K, W = args.steps, max(args.warmup, 1)
+    run, kind, threads = reference_runner("prior3")
+    per_step = 32          # bounded sample of the workload per step (the reference cannot batch)
+    for i in range(W * 4):
+        run(i)
+    t0 = time.perf_counter()
+    for s in range(K):
+        for i in range(per_step):
+            run(s * per_step + i)
+    dt = time.perf_counter() - t0
+    v = K * per_step / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"3-block UAHN (traced_model_3_blocks_using_prior), {per_step} sequential batch-1 "
+                                   "pairs per step on host CPU", "pairs_per_step": per_step, "variant": "prior3",
+                       "torch": torch.__version__},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": f"{K} steps x {per_step} sequential batch-1 forwards, libtorch CPU, {threads} threads"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cuahn_vio_b200 import api, build, synthetic as S, weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    wfile = weights.synthetic_weights_file(0)
+
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    chunk = args.chunk or B
+    n_sets = 3                                    # rotate input sets: 3 x 147 MB of u8 frames  > 126 MB L2
+    hp, hc, _, hprior = S.tiled_batch(B, unique=32, base_seed=20240 + 1000 * rank)
+    stream = torch.cuda.current_stream()
+    net = api.Uahn(wfile, "prior3", show_error=False, precision=args.precision, device=local, max_batch=chunk,
+                   stream=stream.cuda_stream)
+    sets = []
+    for s in range(n_sets):
+        roll = s * 7
+        sets.append((torch.from_numpy(np.roll(hp, roll, 0)).to(dev), torch.from_numpy(np.roll(hc, roll, 0)).to(dev),
+                     torch.from_numpy(np.roll(hprior, roll, 0).reshape(B, 8)).to(dev)))
+    mean = torch.empty(B, 8, device=dev)
+    cov = torch.empty(B, 64, device=dev)
+
+    def step(i):
+        p, c, pr = sets[i % n_sets]
+        for o in range(0, B, chunk):
+            n = min(chunk, B - o)
+            net.infer_batch_ptrs(n, p[o:].data_ptr(), c[o:].data_ptr(), pr[o:].data_ptr(), mean[o:].data_ptr(),
+                                 cov[o:].data_ptr(), seed=1, first_pair=rank * B + o)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    net.profile_enable(True)
+    l0 = net.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        step(W + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = net.launch_count - l0
+    prof_ms, prof_cnt = net.profile_read()
+    net.profile_enable(False)
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * K / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------------------
+    php = torch.from_numpy(hp).pin_memory()
+    phc = torch.from_numpy(hc).pin_memory()
+    ppr = torch.from_numpy(hprior.reshape(B, 8)).pin_memory()
+    hmean = torch.empty(B, 8).pin_memory()
+    hcov = torch.empty(B, 64).pin_memory()
+
+    def step_e2e(i):
+        for o in range(0, B, chunk):
+            n = min(chunk, B - o)
+            net.infer_batch_ptrs(n, php[o:].data_ptr(), phc[o:].data_ptr(), ppr[o:].data_ptr(), hmean[o:].data_ptr(),
+                                 hcov[o:].data_ptr(), seed=1, first_pair=rank * B + o, device=False)
+    Ke = max(3, min(K, 10))
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * Ke / float(te.item())
+    # results of the two paths must agree (same seed / pair indices)
+    same = bool(torch.equal(hmean.to(dev), mean))
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    conv_ms_per_step = prof_ms[1] / K
+    tensor_flops = 2.0 * CONV_MACS * B
+    achieved = tensor_flops / (conv_ms_per_step * 1e-3) / 1e12 if conv_ms_per_step > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"3-block UAHN (traced_model_3_blocks_using_prior) over {B} synthetic pairs per GPU "
+                               f"per step ({8192 if world == 8 and B == 1024 else world * B} pairs sharded by sequence over {world} GPU)",
+                   "variant": "prior3", "pairs_per_gpu_per_step": B, "pairs_per_call": chunk,
+                   "precision": args.precision, "weights": "synthetic seed 0 (reference checkpoint not shipped)",
+                   "l2": f"inputs rotate over {n_sets} resident sets of {2 * B * 71680 / 1e6:.0f} MB (> 126 MB L2); "
+                         f"activations {('3.65' if args.precision == 'bf16' else '7.3')} MB/pair stream through HBM",
+                   "parallelism": f"independent pairs, {world} shard(s), no data-path collective"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (2 * 71680 + 32),
+                "d2h_bytes_per_step": B * 72 * 4, "steps": Ke, "matches_device_path": same},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "kernel": "conv implicit-GEMM (17 launches per step: blocks 2,3,4)",
+                     "algorithmic_flops_per_launch_group": tensor_flops, "ms_per_step": conv_ms_per_step,
+                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})"},
+        "stage_ms_per_step": {"warp_concat_pool": prof_ms[0] / K, "conv_stacks": prof_ms[1] / K,
+                              "mc_head_gemm": prof_ms[2] / K, "fc_dlt_mc_small": prof_ms[3] / K},
+        "stage_launches_per_step": {k: int(v // K) for k, v in zip(("warp", "conv", "mc_gemm", "small"), prof_cnt)},
+        "hbm": {"kernel": "warp+concat+pool (3 launches per step)", "algorithmic_bytes_per_step": 3 * WARP_BYTES * B,
+                "achieved_gbs": (3 * WARP_BYTES * B / (prof_ms[0] / K * 1e-3) / 1e9) if prof_ms[0] > 0 else None,
+                "peak_gbs": peaks["hbm_gbs"], "layout": "fp32 in/out as in the reference (573 440 B per warp)"},
+    }
+    if line["hbm"]["achieved_gbs"]:
+        line["hbm"]["frac"] = line["hbm"]["achieved_gbs"] / peaks["hbm_gbs"]
+
+    # ---- p50 batch-1 latency (BASELINE.json configs[1]: full cascade, no prior) -------------------------
+    if not args.no_latency and world == 1:
+        lat = {}
+        for variant in ("full", "prior3"):
+            with api.Uahn(wfile, variant, precision=args.precision, device=local, max_batch=1) as n1:
+                n1.load_image(hp[0], 0.0)
+                n1.load_image(hc[0], 1.0)
+                pr = hprior[0].reshape(8).astype(np.float64) if variant == "prior3" else None
+                for i in range(50):
+                    n1.infer(pr, seed=1, pair_index=i)
+                ts = []
+                for i in range(500):
+                    t0 = time.perf_counter()
+                    n1.infer(pr, seed=1, pair_index=i)
+                    ts.append(time.perf_counter() - t0)
+                ts.sort()
+                lat[variant] = {"p50_ms": 1e3 * ts[len(ts) // 2], "p90_ms": 1e3 * ts[int(len(ts) * 0.9)],
+                                "p99_ms": 1e3 * ts[int(len(ts) * 0.99)], "calls": len(ts),
+                                "what": "uahn_infer wall clock: prior H2D + forward + 72-float D2H, frames resident"}
+        line["latency_batch1"] = lat
+
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = time_reference(args.cpu_seconds, "prior3")
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

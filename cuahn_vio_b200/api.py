@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "uahn_create", "uahn_destroy", "uahn_last_error", "uahn_load_image", "uahn_infer", "uahn_infer_batch",
     "uahn_infer_batch_device", "uahn_synchronize", "uahn_stream", "uahn_launch_count",
     "uahn_latest_inference_time", "uahn_image_count", "uahn_philox_keep_masks", "uahn_stage_dlt",
-    "uahn_stage_warp", "uahn_debug_read",
+    "uahn_stage_warp", "uahn_debug_read", "uahn_profile_enable", "uahn_profile_read",
 ]
 
 
@@ -78,6 +78,10 @@ def load_library(path: str | None = None):
     lib.uahn_stage_dlt.restype = i
     lib.uahn_stage_warp.argtypes = [vp, i, vp, vp, vp, vp, vp]
     lib.uahn_stage_warp.restype = i
+    lib.uahn_profile_enable.argtypes = [vp, i]
+    lib.uahn_profile_enable.restype = i
+    lib.uahn_profile_read.argtypes = [vp, vp, vp]
+    lib.uahn_profile_read.restype = i
     lib.uahn_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.uahn_debug_read.restype = C.c_long
     if path is None:
@@ -199,6 +203,15 @@ class Uahn:
     @property
     def latest_inference_time(self) -> float:
         return float(self._lib.uahn_latest_inference_time(self._h))
+
+    def profile_enable(self, on: bool = True):
+        self._check(self._lib.uahn_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """→ (ms[4], launches[4]) per category: 0 warp/error-map, 1 conv stacks, 2 MC-head GEMMs, 3 small head kernels."""
+        ms, cnt = np.zeros(4, np.float64), np.zeros(4, np.uint64)
+        self._check(self._lib.uahn_profile_read(self._h, _ptr(ms), _ptr(cnt)))
+        return ms, cnt
 
     # -- stage entry points --------------------------------------------------------------------------
     def stage_dlt(self, offsets: np.ndarray) -> np.ndarray:

@@ -118,6 +118,33 @@ struct uahn_handle {
   int img_counter = 0;
   double latest_time = -1.0;
   int last_n = 0;
+  // per-category device timing (uahn_profile_*)
+  struct ProfSpan { cudaEvent_t a, b; int cat; uint64_t launches; };
+  bool prof_on = false;
+  std::vector<ProfSpan> prof_spans;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[4] = {0, 0, 0, 0};
+  uint64_t prof_launches[4] = {0, 0, 0, 0};
+  int prof_open = -1;
+  uint64_t prof_l0 = 0;
+  cudaEvent_t prof_event() {
+    if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void prof_begin(int cat) {
+    if (!prof_on) return;
+    ProfSpan s{prof_event(), prof_event(), cat, 0};
+    cudaEventRecord(s.a, stream);
+    prof_spans.push_back(s);
+    prof_open = (int)prof_spans.size() - 1;
+    prof_l0 = launches;
+  }
+  void prof_end() {
+    if (!prof_on || prof_open < 0) return;
+    cudaEventRecord(prof_spans[prof_open].b, stream);
+    prof_spans[prof_open].launches = launches - prof_l0;
+    prof_open = -1;
+  }
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -321,27 +348,42 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
   int rc;
   if (variant != UAHN_VARIANT_FULL) {
     if (!prior) return h->fail(UAHN_ERR_INVALID, "this variant needs a prior");
+    h->prof_begin(3);
     LAUNCH(launch_dlt(n, prior, nullptr, h->Hb[0], st));                   // model_to_trace.py:129-130
+    h->prof_end();
     Hcur = h->Hb[0];
   }
   for (int b = 1; b <= 3; ++b) {
     Block& B = h->blocks[b];
     if (!B.active) continue;
     // block 1 sees the raw current image (model_to_trace.py:138-139); blocks 2,3 the warped one (:154,172)
+    h->prof_begin(0);
     LAUNCH(launch_warp_concat_pool<T>(prev, curr, b == 1 ? nullptr : Hcur, B.x, B.pool, n, st));
+    h->prof_end();
+    h->prof_begin(1);
     for (Layer& L : B.layers)
       if ((rc = run_conv<T>(h, L, n))) return rc;
+    h->prof_end();
+    h->prof_begin(3);
     LAUNCH(launch_fc8_dlt<T>(n, (const T*)B.layers.back().out.p, B.W8, B.b8, b == 1 ? nullptr : Hcur, h->Hb[b],
                              h->dblk[b], st));
+    h->prof_end();
     Hcur = h->Hb[b];
   }
   Block& B4 = h->blocks[4];
+  h->prof_begin(0);
   LAUNCH(launch_warp_concat_pool<T>(prev, curr, Hcur, B4.x, 1, n, st));     // model_to_trace.py:261-263
+  h->prof_end();
+  h->prof_begin(1);
   for (Layer& L : B4.layers)
     if ((rc = run_conv<T>(h, L, n))) return rc;
+  h->prof_end();
   const T* feat = (const T*)B4.layers.back().out.p;
   const uint64_t seed = rng ? rng->seed : 0, first = rng ? rng->first_pair_index : 0;
+  h->prof_begin(3);
   LAUNCH(launch_mc_expand<T>(n, feat, (T*)h->mcA, d_masks, seed, first, st));
+  h->prof_end();
+  h->prof_begin(2);
   for (int head = 0; head < 2; ++head) {
     ConvGeom g = dense_geom(n * MC, FC_IN, FC_HID, 1);
     const T* a = (const T*)h->mcA + (size_t)head * n * MC * FC_IN;
@@ -352,10 +394,17 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
       LAUNCH(launch_conv_bf16(head ? h->W1u_b : h->W1m_b, a, head ? h->b1u : h->b1m, o, g, st));
     }
   }
+  h->prof_end();
   const bool want_err = h->cfg.show_error && err;
+  h->prof_begin(3);
   LAUNCH(launch_mc_final<T>(n, (const T*)h->hid, h->W2m, h->b2m, h->W2u, h->b2u, Hcur, d_masks, seed, first, mean, cov,
                             h->cfg.show_error ? h->Htot : nullptr, h->mc_mean, h->mc_logvar, st));
-  if (want_err) LAUNCH(launch_warp_plain(prev, curr, h->Htot, err, nullptr, nullptr, 1, n, st));
+  h->prof_end();
+  if (want_err) {
+    h->prof_begin(0);
+    LAUNCH(launch_warp_plain(prev, curr, h->Htot, err, nullptr, nullptr, 1, n, st));
+    h->prof_end();
+  }
   h->last_n = n;
   return UAHN_OK;
 }
@@ -463,6 +512,8 @@ void uahn_destroy(uahn_handle* h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  for (auto& sp : h->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->h_img) cudaFreeHost(h->h_img);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -574,6 +625,35 @@ int uahn_infer(uahn_handle* h, const double* prior_px, const uahn_rng* rng, doub
       v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
       err_map[i] = (uint8_t)v;
     }
+  return UAHN_OK;
+}
+
+int uahn_profile_enable(uahn_handle* h, int on) {
+  if (!h) return UAHN_ERR_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  for (auto& sp : h->prof_spans) { h->prof_pool.push_back(sp.a); h->prof_pool.push_back(sp.b); }
+  h->prof_spans.clear();
+  for (int i = 0; i < 4; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+  h->prof_on = on != 0;
+  return UAHN_OK;
+}
+
+int uahn_profile_read(uahn_handle* h, double* ms4, uint64_t* launches4) {
+  if (!h || !ms4) return UAHN_ERR_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  for (auto& sp : h->prof_spans) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    h->prof_ms[sp.cat] += ms;
+    h->prof_launches[sp.cat] += sp.launches;
+    h->prof_pool.push_back(sp.a);
+    h->prof_pool.push_back(sp.b);
+  }
+  h->prof_spans.clear();
+  for (int i = 0; i < 4; ++i) {
+    ms4[i] = h->prof_ms[i];
+    if (launches4) launches4[i] = h->prof_launches[i];
+  }
   return UAHN_OK;
 }
 

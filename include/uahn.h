@@ -114,6 +114,14 @@ UAHN_API uint64_t uahn_launch_count(const uahn_handle* h);
 UAHN_API double uahn_latest_inference_time(const uahn_handle* h); /* HomographyNet::get_latest_inference_time */
 UAHN_API int uahn_image_count(const uahn_handle* h);               /* HomographyNet::img_counter */
 
+/* Per-stage device timing (bench.py's roofline): when enabled, every forward brackets each kernel group with
+ * CUDA events on the handle's stream.  Categories: 0 = warp/concat/pool + error map (HBM-bound),
+ * 1 = conv stacks (tensor-bound), 2 = MC-head 5120->256 GEMMs (tensor-bound), 3 = FC8+DLT / MC expand / final.
+ * uahn_profile_read synchronises, adds the elapsed ms of all finished groups into ms[4] / launches[4]
+ * (accumulating since the last uahn_profile_enable(h, 1)) and returns UAHN_OK. */
+UAHN_API int uahn_profile_enable(uahn_handle* h, int on);
+UAHN_API int uahn_profile_read(uahn_handle* h, double* ms4, uint64_t* launches4);
+
 /* Host replica of the in-kernel Philox mask generator: fills UAHN_MASK_BYTES_PER_PAIR bytes for one pair. */
 UAHN_API int uahn_philox_keep_masks(uint64_t seed, uint64_t pair_index, uint8_t* out);
 

@@ -112,7 +112,8 @@ def test_e2e_fp32_vs_oracle(api, wfile, synth_sd, variant, show):
         m, c, e = net.infer_batch(prev, curr, pr, keep_masks=_pack(api, masks), want_error=show)
         assert np.abs(m - om).max() < FP32_PX, np.abs(m - om).max()
         assert np.abs(c - oc).max() <= 2e-4 * np.abs(oc).max()
-        assert np.abs(c - np.swapaxes(c, 1, 2)).max() == 0          # symmetric (Eigen::Map reads it transposed)
+        # symmetric up to fp32 rounding, like the reference's own H·V·Hᵀ (Eigen::Map reads it transposed)
+        assert np.abs(c - np.swapaxes(c, 1, 2)).max() <= 1e-6 * np.abs(c).max()
         if show:
             assert np.abs(e - oe).max() < 0.05 and np.abs(e - oe).mean() < 1e-3   # 255-scaled grey levels
         # stage taps vs the oracle's taps for pair 0
