@@ -226,7 +226,8 @@ def run_ours(args):
     chunk = args.chunk or B
     n_sets = 3                                    # rotate input sets: 3 x 147 MB of u8 frames  > 126 MB L2
     hp, hc, _, hprior = S.tiled_batch(B, unique=32, base_seed=20240 + 1000 * rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(dev)      # non-default stream shared by torch events and the library's launches
+    torch.cuda.set_stream(stream)
     net = api.Uahn(wfile, "prior3", show_error=False, precision=args.precision, device=local, max_batch=chunk,
                    stream=stream.cuda_stream)
     sets = []
@@ -300,7 +301,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * Ke / float(te.item())
-    # results of the two paths must agree (same seed / pair indices)
+    # results of the two paths must agree (same inputs, seed and pair indices)
+    p0, c0, pr0 = (torch.from_numpy(a).to(dev) for a in (hp, hc, hprior.reshape(B, 8)))
+    for o in range(0, B, chunk):
+        n = min(chunk, B - o)
+        net.infer_batch_ptrs(n, p0[o:].data_ptr(), c0[o:].data_ptr(), pr0[o:].data_ptr(), mean[o:].data_ptr(),
+                             cov[o:].data_ptr(), seed=1, first_pair=rank * B + o)
+    torch.cuda.synchronize()
     same = bool(torch.equal(hmean.to(dev), mean))
 
     if rank != 0:

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "uahn_create", "uahn_destroy", "uahn_last_error", "uahn_load_image", "uahn_infer", "uahn_infer_batch",
     "uahn_infer_batch_device", "uahn_synchronize", "uahn_stream", "uahn_launch_count",
     "uahn_latest_inference_time", "uahn_image_count", "uahn_philox_keep_masks", "uahn_stage_dlt",
-    "uahn_stage_warp", "uahn_debug_read", "uahn_profile_enable", "uahn_profile_read",
+    "uahn_stage_warp", "uahn_debug_read", "uahn_profile_enable", "uahn_profile_read", "uahn_stage_conv",
 ]
 
 
@@ -82,6 +82,8 @@ def load_library(path: str | None = None):
     lib.uahn_profile_enable.restype = i
     lib.uahn_profile_read.argtypes = [vp, vp, vp]
     lib.uahn_profile_read.restype = i
+    lib.uahn_stage_conv.argtypes = [vp, C.c_char_p, i, vp]
+    lib.uahn_stage_conv.restype = i
     lib.uahn_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.uahn_debug_read.restype = C.c_long
     if path is None:
@@ -228,6 +230,12 @@ class Uahn:
         ix, iy = np.empty((n, IMG_H, IMG_W), np.int16), np.empty((n, IMG_H, IMG_W), np.int16)
         self._check(self._lib.uahn_stage_warp(self._h, n, _ptr(img), _ptr(H), _ptr(out), _ptr(ix), _ptr(iy)))
         return out, ix, iy
+
+    def stage_conv(self, layer: str, x: np.ndarray, out_shape) -> np.ndarray:
+        """Run one Conv2d+LeakyReLU layer (x: n x Cin x H x W float32) → n x Cout x Ho x Wo."""
+        x = np.ascontiguousarray(x, np.float32)
+        self._check(self._lib.uahn_stage_conv(self._h, layer.encode(), x.shape[0], _ptr(x)))
+        return self.debug_read("act:" + layer, (x.shape[0],) + tuple(out_shape))
 
     def debug_read(self, what: str, shape) -> np.ndarray:
         out = np.empty(shape, np.float32)

@@ -1,11 +1,431 @@
+// bf16 implicit-GEMM convolution on the sm_100a tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+//   D[m][n] = sum_k A[m][k] * B[n][k]      M = output pixel groups, N = XB * Cout, K = KH * run
+//
+// * A (activations) is never materialised: zero-haloed NHWC makes the im2col row of an output pixel a set of
+//   KH contiguous byte runs (one per kernel row), so the producer warps gather 16-byte granules with
+//   cp.async (zero-fill for tail rows) straight into the 128B-swizzled K-major shared-memory layout the
+//   UMMA descriptor expects.
+// * "Toeplitz" expansion along x: one GEMM row can cover XB consecutive output pixels; its K run is the union
+//   of their receptive fields and B holds the correspondingly shifted (banded) filter copies.  This is what
+//   lets the 2-channel 7x7 first layers (Cin*2 B = 4 B per pixel, far below a 16 B granule) and the thin
+//   Cout = 8/16/32 layers fill a 128 x N tensor-core tile: N = XB*Cout.
+// * B (weights) is prepared once on the host as the exact shared-memory image of every K stage, so a stage
+//   is one cp.async.bulk (TMA bulk copy, UBLKCP) completing on the stage's mbarrier.
+// * Warp roles: warps 0-3 gather A then run the epilogue (tcgen05.ld -> bias + LeakyReLU -> bf16 -> global),
+//   warp 4 issues tcgen05.mma from one elected lane, warp 5 streams B.  Full/empty mbarriers per stage;
+//   tcgen05.commit releases a stage when the MMAs that read it retire.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 #include "conv_bf16.h"
+
 namespace uahn {
-int conv_bf16_prepare(ConvBf16Weights&, const std::vector<float>&, const std::vector<float>&, const ConvGeom&,
-                      const Tensor&, const Tensor&, std::vector<void*>&, std::string& err) {
-  err = "bf16 path not built yet";
-  return -5;
+namespace {
+
+constexpr int BM = 128;                 // UMMA M
+constexpr int STAGE_K = 64;             // bf16 elements per K stage = 128 B = one swizzle row
+constexpr int A_STAGE_BYTES = BM * 128;
+constexpr int IG_THREADS = 192;
+constexpr int LAG = 2;                  // cp.async groups in flight per producer thread
+
+struct IgemmParams {
+  const uint8_t* in;        // activation base
+  const uint8_t* b_image;   // [k_stages][N_total][128 B], SW128 K-major
+  const float* bias_x;      // [N_total]
+  uint8_t* out;
+  int M_rows, rows_per_img, Wox;
+  long long in_pitch_n_b;
+  int in_pitch_y_b, in_row_step_b, in_col_step_b;
+  long long in_origin_b;
+  int run_granules, total_granules, k_stages, k_steps;
+  long long out_pitch_n_b;
+  int out_pitch_y_b, out_col_step_b;
+  long long out_origin_b;
+  int n_total;
+  int act;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-cudaError_t launch_conv_bf16(const ConvBf16Weights&, const void*, const float*, void*, const ConvGeom&, cudaStream_t) {
-  return cudaErrorNotSupported;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO = 1 (unused),
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::f16: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BN>
+constexpr int tmem_cols() { return BN < 32 ? 32 : BN; }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(IG_THREADS) conv_igemm_bf16_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int B_STAGE_BYTES = BN * 128;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+  // bars[0..S) full, [S..2S) empty, [2S] accumulator ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accbar = smem_u32(bars + 2 * STAGES);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(full0 + 8 * s, 128 + 1);   // 128 gather threads + the B loader's expect_tx arrive
+        mbar_init(empty0 + 8 * s, 1);        // one tcgen05.commit
+      }
+      mbar_init(accbar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)tmem_cols<BN>())
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== A gather (128 threads) =====================
+    const int j = tid & 7, rb = tid >> 3;            // granule column in the stage, first row
+    const uint32_t dst_off = (uint32_t)rb * 128 + (uint32_t)((j ^ (rb & 7)) << 4);
+    uint32_t rowoff[8];
+    uint32_t rowok = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + rb + 16 * i;
+      if (m < p.M_rows) {
+        const int img = m / p.rows_per_img, rem = m - img * p.rows_per_img;
+        const int oy = rem / p.Wox, oxb = rem - oy * p.Wox;
+        rowoff[i] = (uint32_t)(p.in_origin_b + (long long)img * p.in_pitch_n_b + (long long)oy * p.in_row_step_b +
+                               (long long)oxb * p.in_col_step_b);
+        rowok |= 1u << i;
+      } else {
+        rowoff[i] = 0;
+      }
+    }
+    int ky = 0, jj = j;                               // granule (s*8 + j) = ky * run_granules + jj
+    while (jj >= p.run_granules) { jj -= p.run_granules; ++ky; }
+    for (int s = 0; s < p.k_stages; ++s) {
+      const int slot = s % STAGES;
+      mbar_wait(empty0 + 8 * slot, ((s / STAGES) & 1) ^ 1);
+      const bool gvalid = s * 8 + j < p.total_granules;
+      const uint8_t* src = p.in + (long long)ky * p.in_pitch_y_b + jj * 16;
+      const uint32_t dst = smem_u32(sA + slot * A_STAGE_BYTES) + dst_off;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = gvalid && ((rowok >> i) & 1u);
+        cp_async16(dst + i * 16 * 128, ok ? src + rowoff[i] : p.in, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (s >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        mbar_arrive(full0 + 8 * ((s - LAG) % STAGES));
+      }
+      jj += 8;
+      while (jj >= p.run_granules) { jj -= p.run_granules; ++ky; }
+    }
+    // drain: the last min(LAG, k_stages) stages
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int s = max(0, p.k_stages - LAG); s < p.k_stages; ++s) mbar_arrive(full0 + 8 * (s % STAGES));
+
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int m = m0 + row;
+    const bool mok = m < p.M_rows;
+    uint8_t* orow = nullptr;
+    if (mok) {
+      const int img = m / p.rows_per_img, rem = m - img * p.rows_per_img;
+      const int oy = rem / p.Wox, oxb = rem - oy * p.Wox;
+      orow = p.out + p.out_origin_b + (long long)img * p.out_pitch_n_b + (long long)oy * p.out_pitch_y_b +
+             (long long)oxb * p.out_col_step_b + (long long)n0 * 2;
+    }
+    constexpr int CHUNKS = BN / 16;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 16), r);
+      tmem_ld_wait();
+      if (mok) {
+        uint32_t packed[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float v0 = __uint_as_float(r[2 * q]) + __ldg(p.bias_x + n0 + c * 16 + 2 * q);
+          float v1 = __uint_as_float(r[2 * q + 1]) + __ldg(p.bias_x + n0 + c * 16 + 2 * q + 1);
+          if (p.act) { v0 = lrelu(v0); v1 = lrelu(v1); }
+          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+          packed[q] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint4* o = reinterpret_cast<uint4*>(orow + c * 32);
+        o[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        o[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    for (int s = 0; s < p.k_stages; ++s) {
+      const int slot = s % STAGES;
+      mbar_wait(full0 + 8 * slot, (s / STAGES) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + slot * A_STAGE_BYTES));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + slot * B_STAGE_BYTES));
+        const int ksteps = min(4, p.k_steps - s * 4);
+        for (int kk = 0; kk < ksteps; ++kk)   // +32 B along K inside the swizzle row = +2 in descriptor units
+          tc_mma_bf16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (s | kk) != 0 ? 1u : 0u);
+        tc_commit(empty0 + 8 * slot);
+        if (s == p.k_stages - 1) tc_commit(accbar);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  } else {
+    // ===================== B loader (warp 5) =====================
+    if (lane == 0) {
+      for (int s = 0; s < p.k_stages; ++s) {
+        const int slot = s % STAGES;
+        mbar_wait(empty0 + 8 * slot, ((s / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(full0 + 8 * slot, B_STAGE_BYTES);
+        bulk_g2s(smem_u32(sB + slot * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES,
+                 full0 + 8 * slot);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)tmem_cols<BN>())
+                 : "memory");
+  }
+}
+
+template <int BN, int STAGES>
+cudaError_t launch_t(const IgemmParams& p, cudaStream_t st) {
+  constexpr size_t smem = 1024 + (size_t)STAGES * (A_STAGE_BYTES + BN * 128) + (2 * STAGES + 1) * 8 + 16;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_bf16_kernel<BN, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dim3 grid((p.M_rows + BM - 1) / BM, p.n_total / BN);
+  conv_igemm_bf16_kernel<BN, STAGES><<<grid, IG_THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+inline uint16_t f2bf(float f) {   // round-to-nearest-even, like __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+}  // namespace
+
+// Choose XB (output pixels per GEMM row) for a layer.  Constraints: XB divides Wo; the run start must be
+// 16-byte aligned (XB*stride*Cin*2 % 16 == 0); N = XB*Cout in [16, 256], multiple of 16.
+static int choose_xb(const ConvGeom& g) {
+  if (g.KH == 1 && g.KW == 1) return 1;
+  int best = 0;
+  double best_cost = 1e30;
+  for (int xb = 1; xb <= 16; xb *= 2) {
+    if (g.Wo % xb) continue;
+    if ((xb * g.stride * g.Cin * 2) % 16) continue;
+    const int n = xb * g.Cout;
+    if (n < 16 || n > 256 || n % 16) continue;
+    const int run_elems = (g.stride * (xb - 1) + g.KW) * g.Cin;
+    const int rlg = (run_elems + 7) / 8;
+    const int stages = (g.KH * rlg + 7) / 8;
+    const double rows = (double)g.Ho * g.Wo / xb;
+    // per 128-row tile and K stage: gather ~256 cycles (LDGSTS issue), MMA 2N cycles (SURVEY/DESIGN cost model)
+    const double cost = rows / 128.0 * stages * std::max(256.0, 2.0 * n);
+    if (cost < best_cost) { best_cost = cost; best = xb; }
+  }
+  return best;
+}
+
+int conv_bf16_prepare(ConvBf16Weights& wb, const std::vector<float>& wk, const std::vector<float>& bias,
+                      const ConvGeom& g, const Tensor& in, const Tensor& out, std::vector<void*>& allocs,
+                      std::string& err) {
+  (void)in; (void)out;
+  const int xb = choose_xb(g);
+  if (!xb) { err = "no valid Toeplitz factor"; return -1; }
+  if (g.Cin % 8 && !(g.Cin == 2 && (xb * g.stride) % 4 == 0)) { err = "unsupported Cin"; return -1; }
+  const int n_total = xb * g.Cout;
+  const int run_elems = (g.stride * (xb - 1) + g.KW) * g.Cin;
+  const int rlg = (run_elems + 7) / 8;
+  const int total_granules = g.KH * rlg;
+  const int k_steps = (total_granules + 1) / 2;
+  const int k_stages = (k_steps + 3) / 4;
+  std::vector<uint16_t> img((size_t)k_stages * n_total * 64, 0);
+  for (int ky = 0; ky < g.KH; ++ky)
+    for (int q = 0; q < rlg * 8; ++q) {
+      const int xi = q / g.Cin, c = q % g.Cin;
+      const int kidx = (ky * rlg) * 8 + q;              // K index inside the GEMM
+      const int s = kidx / 64, kk = kidx % 64;
+      for (int xo = 0; xo < xb; ++xo) {
+        const int kx = xi - xo * g.stride;
+        if (kx < 0 || kx >= g.KW) continue;
+        for (int co = 0; co < g.Cout; ++co) {
+          const int n = xo * g.Cout + co;
+          const float w = wk[(size_t)((ky * g.KW + kx) * g.Cin + c) * g.Cout + co];
+          const size_t byte = ((size_t)s * n_total + n) * 128 + (size_t)((((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2);
+          img[byte / 2] = f2bf(w);
+        }
+      }
+    }
+  void* d = nullptr;
+  if (cudaMalloc(&d, img.size() * 2) != cudaSuccess) { err = "cudaMalloc(B image)"; return -2; }
+  allocs.push_back(d);
+  if (cudaMemcpy(d, img.data(), img.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { err = "memcpy(B image)"; return -2; }
+  std::vector<float> bx((size_t)n_total);
+  for (int xo = 0; xo < xb; ++xo)
+    for (int co = 0; co < g.Cout; ++co) bx[(size_t)xo * g.Cout + co] = bias[co];
+  void* db = nullptr;
+  if (cudaMalloc(&db, bx.size() * 4) != cudaSuccess) { err = "cudaMalloc(bias)"; return -2; }
+  allocs.push_back(db);
+  if (cudaMemcpy(db, bx.data(), bx.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { err = "memcpy(bias)"; return -2; }
+  wb.b_image = d;
+  wb.bias_x = (float*)db;
+  wb.xb = xb;
+  wb.n_total = n_total;
+  wb.k_total = k_stages * 64;
+  wb.runs = g.KH;
+  wb.run_granules = rlg;
+  wb.ready = 1;
+  return 0;
+}
+
+cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const float* bias, void* out,
+                             const ConvGeom& g, cudaStream_t st) {
+  (void)bias;
+  if (!wb.ready) return cudaErrorInvalidValue;
+  IgemmParams p{};
+  const int xb = wb.xb;
+  p.in = (const uint8_t*)in;
+  p.b_image = (const uint8_t*)wb.b_image;
+  p.bias_x = wb.bias_x;
+  p.out = (uint8_t*)out;
+  p.Wox = g.Wo / xb;
+  p.rows_per_img = g.Ho * p.Wox;
+  p.M_rows = g.M / xb;
+  p.in_pitch_n_b = g.in_pitch_n * 2;
+  p.in_pitch_y_b = (int)(g.in_pitch_y * 2);
+  p.in_row_step_b = (int)(g.stride * g.in_pitch_y * 2);
+  p.in_col_step_b = xb * g.stride * g.Cin * 2;
+  p.in_origin_b = g.in_origin * 2;
+  p.run_granules = wb.run_granules;
+  p.total_granules = wb.runs * wb.run_granules;
+  p.k_steps = (p.total_granules + 1) / 2;
+  p.k_stages = (p.k_steps + 3) / 4;
+  p.out_pitch_n_b = g.out_pitch_n * 2;
+  p.out_pitch_y_b = (int)(g.out_pitch_y * 2);
+  p.out_col_step_b = xb * g.Cout * 2;
+  p.out_origin_b = g.out_origin * 2;
+  p.n_total = wb.n_total;
+  p.act = g.act;
+  // 32-bit gather offsets
+  const long long n_img = (g.M + (long long)g.Ho * g.Wo - 1) / ((long long)g.Ho * g.Wo);
+  if (n_img * p.in_pitch_n_b >= (1ll << 32)) return cudaErrorInvalidValue;
+  const int m_tiles = (p.M_rows + BM - 1) / BM;
+  // N tile: the whole N when the grid is already wide, narrower tiles for the small-M tail layers
+  int bn = std::min(p.n_total, 256);
+  while (bn > 64 && (long long)m_tiles * (p.n_total / bn) < 148 * 2) bn /= 2;
+  switch (bn) {
+    case 256: return launch_t<256, 3>(p, st);
+    case 128: return launch_t<128, 3>(p, st);
+    case 64: return launch_t<64, 4>(p, st);
+    case 32: return launch_t<32, 4>(p, st);
+    case 16: return launch_t<16, 4>(p, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 }  // namespace uahn

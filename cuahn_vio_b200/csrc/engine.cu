@@ -710,6 +710,39 @@ int uahn_stage_warp(uahn_handle* h, int n, const uint8_t* img, const float* Hm, 
   return UAHN_OK;
 }
 
+int uahn_stage_conv(uahn_handle* h, const char* layer, int n, const float* in_nchw) {
+  if (!h || !layer || !in_nchw) return UAHN_ERR_INVALID;
+  if (n <= 0 || n > h->cap) return h->fail(UAHN_ERR_INVALID, "n outside [1, max_batch]");
+  CK(cudaSetDevice(h->cfg.device));
+  Layer* L = nullptr;
+  for (int b = 1; b <= 4 && !L; ++b)
+    for (auto& l : h->blocks[b].layers)
+      if (h->blocks[b].active && !strcmp(layer, l.spec.name)) L = &l;
+  if (!L) return h->fail(UAHN_ERR_INVALID, "layer '%s' not in this variant", layer);
+  const Tensor& t = L->in;
+  std::vector<uint8_t> raw((size_t)n * t.pitch_n * h->es, 0);
+  for (int i = 0; i < n; ++i)
+    for (int c = 0; c < t.C; ++c)
+      for (int y = 0; y < t.H; ++y)
+        for (int x = 0; x < t.W; ++x) {
+          const float v = in_nchw[(((size_t)i * t.C + c) * t.H + y) * t.W + x];
+          const size_t dst = (size_t)t.off(i, y, x, c);
+          if (h->bf16) {
+            uint32_t u; memcpy(&u, &v, 4);
+            u += 0x7fffu + ((u >> 16) & 1u);
+            reinterpret_cast<uint16_t*>(raw.data())[dst] = (uint16_t)(u >> 16);
+          } else {
+            reinterpret_cast<float*>(raw.data())[dst] = v;
+          }
+        }
+  CK(cudaMemcpyAsync(t.p, raw.data(), raw.size(), cudaMemcpyHostToDevice, h->stream));
+  int rc = h->bf16 ? run_conv<__nv_bfloat16>(h, *L, n) : run_conv<float>(h, *L, n);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->last_n = n;
+  return UAHN_OK;
+}
+
 long uahn_debug_read(uahn_handle* h, const char* what, float* out, size_t capacity) {
   if (!h || !what || !out) return UAHN_ERR_INVALID;
   const int n = h->last_n;

@@ -131,6 +131,9 @@ UAHN_API int uahn_stage_dlt(uahn_handle* h, int n, const float* offsets, float* 
 /* warp.py:60-79: img n x 224 x 320 u8, H n x 9 -> out n x 224 x 320 float; optional NW tap indices. */
 UAHN_API int uahn_stage_warp(uahn_handle* h, int n, const uint8_t* img, const float* H, float* out, int16_t* ix_nw,
                     int16_t* iy_nw);
+/* One Conv2d+LeakyReLU layer of the handle's precision path: `layer` e.g. "block_3_1"; in: n x Cin x Hin x Win
+ * float (NCHW); the result is read back with uahn_debug_read("act:<layer>") as n x Cout x Ho x Wo. */
+UAHN_API int uahn_stage_conv(uahn_handle* h, const char* layer, int n, const float* in_nchw);
 /* Values captured during the LAST uahn_infer_batch* call.  what: "H<b>" (n x 9, cumulative after block b;
  * "H0" = prior), "d<b>" (n x 8), "feat<b>" (n x 5120 in NCHW flatten order), "x<b>" (block input,
  * n x 2 x h x w), "mcmean"/"mclogvar" (n x 16 x 8).  Returns number of floats written or <0. */
