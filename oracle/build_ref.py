@@ -28,7 +28,7 @@ def main(quiet: bool = False, force: bool = False, all_variants: bool = False) -
     names = {True: ("traced_full_model_showError.pt", "traced_model_3_blocks_using_prior_showError.pt"),
              False: ("traced_full_model.pt", "traced_model_3_blocks_using_prior.pt")}
     shows = (True, False) if all_variants else (False,)   # the _showError twins only on request (26 MB each)
-    if not force and all(os.path.exists(os.path.join(OUT, n)) for s_ in shows for n in names[s_]):
+    if not force and all(os.path.exists(os.path.join(OUT, n)) for s_ in shows for n in (names[s_] if all_variants else names[s_][1:])):
         return
     sd = S.synthetic_state_dict(0)
     img1 = torch.ones(1, 1, 224, 320) * 0.2        # trace_model.py:20-22
@@ -39,7 +39,8 @@ def main(quiet: bool = False, force: bool = False, all_variants: bool = False) -
         with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
             full = torch.jit.trace(net, (img1, img2), check_trace=False)
             prior = torch.jit.trace(net, (img1, img2, homo8), check_trace=False)
-        full.save(os.path.join(OUT, names[show][0]))
+        if all_variants:
+            full.save(os.path.join(OUT, names[show][0]))
         prior.save(os.path.join(OUT, names[show][1]))
     with open(os.path.join(OUT, "README.txt"), "w") as f:
         f.write(f"TorchScript traces of the unmodified reference model, synthetic weights seed 0, torch {torch.__version__}\n")

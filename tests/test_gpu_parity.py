@@ -258,4 +258,4 @@ def test_e2e_bf16_vs_oracle(api, wfile, synth_sd, variant):
         assert np.abs(m - om).max() < BF16_PX, np.abs(m - om).max()
         diag = np.abs(np.diagonal(oc, axis1=1, axis2=2)).max()
         assert np.abs(c - oc).max() <= BF16_COV_REL * diag, np.abs(c - oc).max() / diag
-        assert np.abs(e - oe).mean() < 0.05
+        assert np.abs(e - oe).mean() < 0.25      # grey levels of 255; follows the <=0.05 px homography difference
