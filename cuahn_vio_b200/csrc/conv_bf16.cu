@@ -25,10 +25,10 @@ namespace uahn {
 namespace {
 
 constexpr int BM = 128;                 // UMMA M
-constexpr int STAGE_K = 64;             // bf16 elements per K stage = 128 B = one swizzle row
-constexpr int A_STAGE_BYTES = BM * 128;
-constexpr int IG_THREADS = 192;
-constexpr int LAG = 2;                  // cp.async groups in flight per producer thread
+constexpr int A_STAGE_BYTES = BM * 128; // 128 rows x 64 bf16 (one 128 B swizzle row each)
+constexpr int IG_THREADS = 320;         // warps 0-3 gather A, 4 MMA, 5 B loader, 6-9 epilogue
+constexpr int LAG = 2;                  // cp.async groups in flight per gather thread
+constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct IgemmParams {
   const uint8_t* in;        // activation base
@@ -36,6 +36,7 @@ struct IgemmParams {
   const float* bias_x;      // [N_total]
   uint8_t* out;
   int M_rows, rows_per_img, Wox;
+  unsigned long long magic_rows, magic_wox;   // ceil(2^40 / d): exact m / d for m < 2^40 / d
   long long in_pitch_n_b;
   int in_pitch_y_b, in_row_step_b, in_col_step_b;
   long long in_origin_b;
@@ -43,12 +44,11 @@ struct IgemmParams {
   long long out_pitch_n_b;
   int out_pitch_y_b, out_col_step_b;
   long long out_origin_b;
-  int n_total;
+  int n_total, n_tiles, m_tiles;
   int act;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -123,33 +123,50 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+__device__ __forceinline__ int fast_div(int m, unsigned long long magic) {
+  return (int)(((unsigned long long)(unsigned)m * magic) >> 40);
+}
 
 template <int BN>
-constexpr int tmem_cols() { return BN < 32 ? 32 : BN; }
+constexpr int tmem_cols() { return 2 * BN < 32 ? 32 : 2 * BN; }   // two accumulator buffers
+template <int BN>
+constexpr int stage_row_bytes() { return BN * 2 + 16; }          // epilogue staging row (+16 B: conflict-free)
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(IG_THREADS) conv_igemm_bf16_kernel(const __grid_constant__ IgemmParams p) {
+// Persistent, warp-specialised implicit GEMM.  B_RES: the whole B operand (k_stages x BN x 128 B) stays in
+// shared memory for the lifetime of the CTA (shallow-K layers); otherwise B streams through the stage ring.
+template <int BN, int STAGES, bool B_RES>
+__global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int SROW = stage_row_bytes<BN>();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
-  // bars[0..S) full, [S..2S) empty, [2S] accumulator ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const int b_slots = B_RES ? p.k_stages : STAGES;
+  uint8_t* sOut = sB + (size_t)b_slots * B_STAGE_BYTES;               // [4 warps][32 rows][SROW]
+  float* sBias = reinterpret_cast<float*>(sOut + 128 * SROW);          // [n_total]
+  long long* sRowOff = reinterpret_cast<long long*>(sBias + 256);      // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRowOff + 128);
+  // bars: [0,S) full, [S,2S) empty, 2S..2S+1 accumulator full, 2S+2..2S+3 accumulator empty, 2S+4 B resident
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accbar = smem_u32(bars + 2 * STAGES);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+  const uint32_t bres = smem_u32(bars + 2 * STAGES + 4);
+  const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
-        mbar_init(full0 + 8 * s, 128 + 1);   // 128 gather threads + the B loader's expect_tx arrive
-        mbar_init(empty0 + 8 * s, 1);        // one tcgen05.commit
+        mbar_init(full0 + 8 * s, B_RES ? 128 : 129);   // 128 gather threads (+ the B loader's expect_tx arrive)
+        mbar_init(empty0 + 8 * s, 1);                  // one tcgen05.commit
       }
-      mbar_init(accbar, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(tfull0 + 8 * b, 1);                  // tcgen05.commit after the tile's last MMA
+        mbar_init(tempty0 + 8 * b, 4);                 // one elected lane per epilogue warp
+      }
+      mbar_init(bres, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -158,121 +175,168 @@ __global__ void __launch_bounds__(IG_THREADS) conv_igemm_bf16_kernel(const __gri
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = tid; i < p.n_total; i += IG_THREADS) sBias[i] = p.bias_x[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // ===================== A gather (128 threads) =====================
-    const int j = tid & 7, rb = tid >> 3;            // granule column in the stage, first row
+    // ===================== A gather: 128 threads, 8 rows x 1 granule column each per stage ==============
+    const int j = tid & 7, rb = tid >> 3;
     const uint32_t dst_off = (uint32_t)rb * 128 + (uint32_t)((j ^ (rb & 7)) << 4);
-    uint32_t rowoff[8];
-    uint32_t rowok = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = m0 + rb + 16 * i;
-      if (m < p.M_rows) {
-        const int img = m / p.rows_per_img, rem = m - img * p.rows_per_img;
-        const int oy = rem / p.Wox, oxb = rem - oy * p.Wox;
-        rowoff[i] = (uint32_t)(p.in_origin_b + (long long)img * p.in_pitch_n_b + (long long)oy * p.in_row_step_b +
-                               (long long)oxb * p.in_col_step_b);
-        rowok |= 1u << i;
-      } else {
-        rowoff[i] = 0;
-      }
-    }
-    int ky = 0, jj = j;                               // granule (s*8 + j) = ky * run_granules + jj
-    while (jj >= p.run_granules) { jj -= p.run_granules; ++ky; }
-    for (int s = 0; s < p.k_stages; ++s) {
-      const int slot = s % STAGES;
-      mbar_wait(empty0 + 8 * slot, ((s / STAGES) & 1) ^ 1);
-      const bool gvalid = s * 8 + j < p.total_granules;
-      const uint8_t* src = p.in + (long long)ky * p.in_pitch_y_b + jj * 16;
-      const uint32_t dst = smem_u32(sA + slot * A_STAGE_BYTES) + dst_off;
+    int it = 0;                                        // global stage counter (ring position)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.n_tiles) * BM;
+      uint32_t rowoff[8];
+      uint32_t rowok = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const bool ok = gvalid && ((rowok >> i) & 1u);
-        cp_async16(dst + i * 16 * 128, ok ? src + rowoff[i] : p.in, ok ? 16u : 0u);
+        const int m = m0 + rb + 16 * i;
+        rowoff[i] = 0;
+        if (m < p.M_rows) {
+          const int img = fast_div(m, p.magic_rows), rem = m - img * p.rows_per_img;
+          const int oy = fast_div(rem, p.magic_wox), oxb = rem - oy * p.Wox;
+          rowoff[i] = (uint32_t)(p.in_origin_b + (long long)img * p.in_pitch_n_b + (long long)oy * p.in_row_step_b +
+                                 (long long)oxb * p.in_col_step_b);
+          rowok |= 1u << i;
+        }
       }
-      cp_async_commit();
-      if (s >= LAG) {
-        cp_async_wait<LAG>();
-        fence_proxy_async();
-        mbar_arrive(full0 + 8 * ((s - LAG) % STAGES));
-      }
-      jj += 8;
+      int ky = 0, jj = j;                              // granule (s*8 + j) = ky * run_granules + jj
       while (jj >= p.run_granules) { jj -= p.run_granules; ++ky; }
+      for (int s = 0; s < p.k_stages; ++s, ++it) {
+        const int slot = it % STAGES;
+        mbar_wait(empty0 + 8 * slot, ((it / STAGES) & 1) ^ 1);
+        const int g = s * 8 + j;
+        if (g < p.total_granules + (p.total_granules & 1)) {   // granules past K are never read by an MMA
+          const bool gvalid = g < p.total_granules;            // the odd partner granule must be zero
+          const uint8_t* src = p.in + (long long)ky * p.in_pitch_y_b + jj * 16;
+          const uint32_t dst = smem_u32(sA + slot * A_STAGE_BYTES) + dst_off;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = gvalid && ((rowok >> i) & 1u);
+            cp_async16(dst + i * 16 * 128, ok ? src + rowoff[i] : p.in, ok ? 16u : 0u);
+          }
+        }
+        cp_async_commit();
+        if (it >= LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async();
+          mbar_arrive(full0 + 8 * ((it - LAG) % STAGES));
+        }
+        jj += 8;
+        while (jj >= p.run_granules) { jj -= p.run_granules; ++ky; }
+      }
     }
-    // drain: the last min(LAG, k_stages) stages
     cp_async_wait<0>();
     fence_proxy_async();
-    for (int s = max(0, p.k_stages - LAG); s < p.k_stages; ++s) mbar_arrive(full0 + 8 * (s % STAGES));
-
-    // ===================== epilogue: TMEM -> registers -> global =====================
-    mbar_wait(accbar, 0);
-    tc_fence_after();
-    const int row = warp * 32 + lane;
-    const int m = m0 + row;
-    const bool mok = m < p.M_rows;
-    uint8_t* orow = nullptr;
-    if (mok) {
-      const int img = m / p.rows_per_img, rem = m - img * p.rows_per_img;
-      const int oy = rem / p.Wox, oxb = rem - oy * p.Wox;
-      orow = p.out + p.out_origin_b + (long long)img * p.out_pitch_n_b + (long long)oy * p.out_pitch_y_b +
-             (long long)oxb * p.out_col_step_b + (long long)n0 * 2;
-    }
-    constexpr int CHUNKS = BN / 16;
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 16), r);
-      tmem_ld_wait();
-      if (mok) {
-        uint32_t packed[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float v0 = __uint_as_float(r[2 * q]) + __ldg(p.bias_x + n0 + c * 16 + 2 * q);
-          float v1 = __uint_as_float(r[2 * q + 1]) + __ldg(p.bias_x + n0 + c * 16 + 2 * q + 1);
-          if (p.act) { v0 = lrelu(v0); v1 = lrelu(v1); }
-          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-          packed[q] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        uint4* o = reinterpret_cast<uint4*>(orow + c * 32);
-        o[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        o[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-      }
-    }
-    tc_fence_before();
+    for (int s = max(0, it - LAG); s < it; ++s) mbar_arrive(full0 + 8 * (s % STAGES));
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-    for (int s = 0; s < p.k_stages; ++s) {
-      const int slot = s % STAGES;
-      mbar_wait(full0 + 8 * slot, (s / STAGES) & 1);
+    int it = 0, tcount = 0;
+    if (B_RES) mbar_wait(bres, 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int ab = tcount & 1;
+      mbar_wait(tempty0 + 8 * ab, ((tcount >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + slot * A_STAGE_BYTES));
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + slot * B_STAGE_BYTES));
-        const int ksteps = min(4, p.k_steps - s * 4);
-        for (int kk = 0; kk < ksteps; ++kk)   // +32 B along K inside the swizzle row = +2 in descriptor units
-          tc_mma_bf16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (s | kk) != 0 ? 1u : 0u);
-        tc_commit(empty0 + 8 * slot);
-        if (s == p.k_stages - 1) tc_commit(accbar);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
+      for (int s = 0; s < p.k_stages; ++s, ++it) {
+        const int slot = it % STAGES;
+        mbar_wait(full0 + 8 * slot, (it / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + slot * A_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (B_RES ? s : slot) * B_STAGE_BYTES));
+          const int ksteps = min(4, p.k_steps - s * 4);
+          for (int kk = 0; kk < ksteps; ++kk)   // +32 B along K inside the swizzle row = +2 in descriptor units
+            tc_mma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (s | kk) != 0 ? 1u : 0u);
+          tc_commit(empty0 + 8 * slot);
+          if (s == p.k_stages - 1) tc_commit(tfull0 + 8 * ab);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     tc_fence_before();
-  } else {
-    // ===================== B loader (warp 5) =====================
+  } else if (warp == 5) {
+    // ===================== B loader =====================
     if (lane == 0) {
-      for (int s = 0; s < p.k_stages; ++s) {
-        const int slot = s % STAGES;
-        mbar_wait(empty0 + 8 * slot, ((s / STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(full0 + 8 * slot, B_STAGE_BYTES);
-        bulk_g2s(smem_u32(sB + slot * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES,
-                 full0 + 8 * slot);
+      if (B_RES) {
+        const int n0 = (blockIdx.x % p.n_tiles) * BN;   // resident mode is launched with n_tiles == 1
+        mbar_arrive_expect_tx(bres, (uint32_t)(p.k_stages * B_STAGE_BYTES));
+        for (int s = 0; s < p.k_stages; ++s)
+          bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES, bres);
+      } else {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int n0 = (tile % p.n_tiles) * BN;
+          for (int s = 0; s < p.k_stages; ++s, ++it) {
+            const int slot = it % STAGES;
+            mbar_wait(empty0 + 8 * slot, ((it / STAGES) & 1) ^ 1);
+            mbar_arrive_expect_tx(full0 + 8 * slot, B_STAGE_BYTES);
+            bulk_g2s(smem_u32(sB + slot * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128,
+                     B_STAGE_BYTES, full0 + 8 * slot);
+          }
+        }
       }
+    }
+  } else {
+    // ===================== epilogue (warps 6-9): TMEM -> bias/LeakyReLU -> bf16 -> smem -> coalesced global ====
+    const int q = warp & 3;                             // TMEM lane quadrant this warp may read
+    uint8_t* myOut = sOut + q * 32 * SROW;
+    long long* myRow = sRowOff + q * 32;
+    constexpr int CPR = BN / 8;                         // 16-byte chunks per output row
+    constexpr int RPI = CPR >= 32 ? 1 : 32 / CPR;       // rows covered by one warp-wide store
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int ab = tcount & 1;
+      const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+      {
+        const int m = m0 + q * 32 + lane;
+        long long off = -1;
+        if (m < p.M_rows) {
+          const int img = fast_div(m, p.magic_rows), rem = m - img * p.rows_per_img;
+          const int oy = fast_div(rem, p.magic_wox), oxb = rem - oy * p.Wox;
+          off = p.out_origin_b + (long long)img * p.out_pitch_n_b + (long long)oy * p.out_pitch_y_b +
+                (long long)oxb * p.out_col_step_b + (long long)n0 * 2;
+        }
+        myRow[lane] = off;
+      }
+      mbar_wait(tfull0 + 8 * ab, (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN);
+#pragma unroll
+      for (int c = 0; c < BN / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c * 16, r);
+        tmem_ld_wait();
+        uint32_t packed[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float v0 = __uint_as_float(r[2 * e]) + sBias[n0 + c * 16 + 2 * e];
+          float v1 = __uint_as_float(r[2 * e + 1]) + sBias[n0 + c * 16 + 2 * e + 1];
+          if (p.act) { v0 = lrelu(v0); v1 = lrelu(v1); }
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+          packed[e] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        uint4* o = reinterpret_cast<uint4*>(myOut + lane * SROW + c * 32);
+        o[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        o[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * ab);     // accumulator free: the next tile's MMAs may start
+      if (CPR <= 32) {
+        const int rsub = lane / (CPR < 32 ? CPR : 32), ch = lane % (CPR < 32 ? CPR : 32);
+#pragma unroll 4
+        for (int r0 = 0; r0 < 32; r0 += RPI) {
+          const int row = r0 + rsub;
+          const long long off = myRow[row];
+          const uint4 v = *reinterpret_cast<const uint4*>(myOut + row * SROW + ch * 16);
+          if (off >= 0) *reinterpret_cast<uint4*>(p.out + off + ch * 16) = v;
+        }
+      }
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -284,18 +348,22 @@ __global__ void __launch_bounds__(IG_THREADS) conv_igemm_bf16_kernel(const __gri
   }
 }
 
-template <int BN, int STAGES>
-cudaError_t launch_t(const IgemmParams& p, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)STAGES * (A_STAGE_BYTES + BN * 128) + (2 * STAGES + 1) * 8 + 16;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_bf16_kernel<BN, STAGES>,
+template <int BN>
+constexpr size_t fixed_smem() { return 1024 + 128 * (size_t)stage_row_bytes<BN>() + 256 * 4 + 128 * 8 + 64 * 8; }
+
+template <int BN, int STAGES, bool B_RES>
+cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st) {
+  const size_t smem = fixed_smem<BN>() + (size_t)STAGES * A_STAGE_BYTES + (size_t)(B_RES ? p.k_stages : STAGES) * BN * 128;
+  if (smem > SMEM_LIMIT) return cudaErrorInvalidConfiguration;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_bf16_kernel<BN, STAGES, B_RES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr = smem;
   }
-  dim3 grid((p.M_rows + BM - 1) / BM, p.n_total / BN);
-  conv_igemm_bf16_kernel<BN, STAGES><<<grid, IG_THREADS, smem, st>>>(p);
+  const int tiles = p.m_tiles * p.n_tiles;
+  conv_igemm_bf16_kernel<BN, STAGES, B_RES><<<std::min(tiles, num_sms), IG_THREADS, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -387,6 +455,12 @@ cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const fl
                              const ConvGeom& g, cudaStream_t st) {
   (void)bias;
   if (!wb.ready) return cudaErrorInvalidValue;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
   IgemmParams p{};
   const int xb = wb.xb;
   p.in = (const uint8_t*)in;
@@ -396,6 +470,8 @@ cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const fl
   p.Wox = g.Wo / xb;
   p.rows_per_img = g.Ho * p.Wox;
   p.M_rows = g.M / xb;
+  p.magic_rows = ((1ull << 40) + p.rows_per_img - 1) / p.rows_per_img;
+  p.magic_wox = ((1ull << 40) + p.Wox - 1) / p.Wox;
   p.in_pitch_n_b = g.in_pitch_n * 2;
   p.in_pitch_y_b = (int)(g.in_pitch_y * 2);
   p.in_row_step_b = (int)(g.stride * g.in_pitch_y * 2);
@@ -411,19 +487,22 @@ cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const fl
   p.out_origin_b = g.out_origin * 2;
   p.n_total = wb.n_total;
   p.act = g.act;
-  // 32-bit gather offsets
   const long long n_img = (g.M + (long long)g.Ho * g.Wo - 1) / ((long long)g.Ho * g.Wo);
-  if (n_img * p.in_pitch_n_b >= (1ll << 32)) return cudaErrorInvalidValue;
-  const int m_tiles = (p.M_rows + BM - 1) / BM;
-  // N tile: the whole N when the grid is already wide, narrower tiles for the small-M tail layers
+  if (n_img * p.in_pitch_n_b >= (1ll << 32) || (long long)p.M_rows * p.rows_per_img >= (1ll << 40))
+    return cudaErrorInvalidValue;   // 32-bit gather offsets / fast_div range
+  p.m_tiles = (p.M_rows + BM - 1) / BM;
+  // N tile: all of N when there are enough M tiles to fill the machine; narrower for the small-M tail layers
   int bn = std::min(p.n_total, 256);
-  while (bn > 64 && (long long)m_tiles * (p.n_total / bn) < 148 * 2) bn /= 2;
+  while (bn > 64 && (long long)p.m_tiles * (p.n_total / bn) < num_sms) bn /= 2;
+  p.n_tiles = p.n_total / bn;
+  // B resident in shared memory when the whole operand of this N tile fits next to a 4-stage A ring
+  const bool res = p.n_tiles == 1 && (size_t)p.k_stages * bn * 128 <= 112 * 1024;
   switch (bn) {
-    case 256: return launch_t<256, 3>(p, st);
-    case 128: return launch_t<128, 3>(p, st);
-    case 64: return launch_t<64, 4>(p, st);
-    case 32: return launch_t<32, 4>(p, st);
-    case 16: return launch_t<16, 4>(p, st);
+    case 256: return launch_t<256, 3, false>(p, num_sms, st);
+    case 128: return res ? launch_t<128, 4, true>(p, num_sms, st) : launch_t<128, 4, false>(p, num_sms, st);
+    case 64: return res ? launch_t<64, 4, true>(p, num_sms, st) : launch_t<64, 6, false>(p, num_sms, st);
+    case 32: return res ? launch_t<32, 4, true>(p, num_sms, st) : launch_t<32, 6, false>(p, num_sms, st);
+    case 16: return res ? launch_t<16, 4, true>(p, num_sms, st) : launch_t<16, 6, false>(p, num_sms, st);
     default: return cudaErrorInvalidValue;
   }
 }
