@@ -271,10 +271,8 @@ def run_ours(args):
     prof_ms, prof_cnt = net.profile_read()
     net.profile_enable(False)
     clk = clocks.stop() if clocks else None
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    from cuahn_vio_b200.sharding import reduce_max_ms
+    ms_max = reduce_max_ms(ms, dev)
     value = world * B * K / (ms_max * 1e-3)
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------------------
@@ -297,10 +295,7 @@ def run_ours(args):
     for i in range(Ke):
         step_e2e(i)
     torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * Ke / float(te.item())
+    e2e_value = world * B * Ke / (reduce_max_ms(1e3 * (time.perf_counter() - t0), dev) * 1e-3)
     # results of the two paths must agree (same inputs, seed and pair indices)
     p0, c0, pr0 = (torch.from_numpy(a).to(dev) for a in (hp, hc, hprior.reshape(B, 8)))
     for o in range(0, B, chunk):

@@ -1,0 +1,48 @@
+"""The C++ drop-in class (include/HomographyNet.h) compiles here; on the GPU box it must agree with the C ABI."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _compile(tmp_path):
+    from cuahn_vio_b200 import build
+    lib = build.build()
+    exe = str(tmp_path / "shim_main")
+    cmd = ["g++", "-std=c++14", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "shim_main.cpp"), "-o", exe, "-L", os.path.dirname(lib), "-luahn",
+           "-Wl,-rpath," + os.path.dirname(lib)]
+    subprocess.run(cmd, check=True, capture_output=True)
+    return exe
+
+
+def test_shim_compiles_and_links(tmp_path):
+    assert os.path.exists(_compile(tmp_path))
+
+
+@pytest.mark.gpu
+def test_shim_matches_c_abi(tmp_path):
+    from cuahn_vio_b200 import api, synthetic as S, weights
+    exe = _compile(tmp_path)
+    wfile = weights.synthetic_weights_file(0)
+    prev, curr, _, prior = S.synthetic_batch(2, start=40)
+    frames = np.stack([prev[0], curr[0], curr[1]])
+    pri = np.stack([prior[0], prior[0], prior[1]]).reshape(3, 8).astype(np.float64)
+    frames.tofile(tmp_path / "frames.u8")
+    pri.tofile(tmp_path / "priors.f64")
+    out = subprocess.run([exe, wfile, str(tmp_path / "frames.u8"), "3", str(tmp_path / "priors.f64"), "0"],
+                         check=True, capture_output=True, text=True).stdout
+    assert "HNet cannot inference! Only has one image!" in out        # HomographyNet.cpp:155-158
+    res = [l.split() for l in out.splitlines() if l.startswith("RESULT")]
+    assert len(res) == 3 and all(float(v) == 0 for v in res[0][4:12])  # first frame: outputs untouched
+    assert [int(r[2]) for r in res] == [1, 2, 3] and float(res[1][3]) == 11.0
+    with api.Uahn(wfile, "prior3", precision="fp32", max_batch=1) as net:
+        # the shim numbers inferences 0,1,... and seeds Philox with (seed=9, pair_index=inference count)
+        m1, c1, _ = net.infer_batch(frames[0:1], frames[1:2], pri[1:2].astype(np.float32), seed=9, first_pair=0)
+        m2, c2, _ = net.infer_batch(frames[1:2], frames[2:3], pri[2:3].astype(np.float32), seed=9, first_pair=1)
+    for r, m, c in ((res[1], m1, c1), (res[2], m2, c2)):
+        assert np.allclose(np.array(r[4:12], float), m[0], atol=1e-6)
+        assert np.allclose(np.array(r[12:20], float), np.diag(c[0]), rtol=1e-6)
