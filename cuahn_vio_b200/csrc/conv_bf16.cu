@@ -17,9 +17,11 @@
 //   tcgen05.commit releases a stage when the MMAs that read it retire.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "conv_bf16.h"
+#include "tc_ptx.cuh"
 
 namespace uahn {
 namespace {
@@ -47,85 +49,6 @@ struct IgemmParams {
   int n_total, n_tiles, m_tiles;
   int act;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO = 1 (unused),
-// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
-}
-// kind::f16: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ int fast_div(int m, unsigned long long magic) {
-  return (int)(((unsigned long long)(unsigned)m * magic) >> 40);
-}
 
 template <int BN>
 constexpr int tmem_cols() { return 2 * BN < 32 ? 32 : 2 * BN; }   // two accumulator buffers
@@ -233,26 +156,36 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
     for (int s = max(0, it - LAG); s < it; ++s) mbar_arrive(full0 + 8 * (s % STAGES));
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
+    // The whole warp runs the (warp-uniform) loop control; only the tcgen05 instructions are predicated on the
+    // elected lane, so descriptors stay in uniform registers and MMAs issue back to back.
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    constexpr uint64_t DESC_HI = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a16_0 = (smem_u32(sA) & 0x3FFFFu) >> 4, b16_0 = (smem_u32(sB) & 0x3FFFFu) >> 4;
+    const int k_stages = p.k_stages, k_steps = p.k_steps;
     int it = 0, tcount = 0;
     if (B_RES) mbar_wait(bres, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int ab = tcount & 1;
       mbar_wait(tempty0 + 8 * ab, ((tcount >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
-      for (int s = 0; s < p.k_stages; ++s, ++it) {
+      const uint32_t d_tmem = tmem_u + (uint32_t)(ab * BN);
+      const bool leader = elect_one();
+      for (int s = 0; s < k_stages; ++s, ++it) {
         const int slot = it % STAGES;
         mbar_wait(full0 + 8 * slot, (it / STAGES) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + slot * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (B_RES ? s : slot) * B_STAGE_BYTES));
-          const int ksteps = min(4, p.k_steps - s * 4);
-          for (int kk = 0; kk < ksteps; ++kk)   // +32 B along K inside the swizzle row = +2 in descriptor units
-            tc_mma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (s | kk) != 0 ? 1u : 0u);
+        const uint32_t alo = a16_0 + (uint32_t)(slot * (A_STAGE_BYTES / 16));
+        const uint32_t blo = b16_0 + (uint32_t)((B_RES ? s : slot) * (B_STAGE_BYTES / 16));
+        const int ksteps = min(4, k_steps - s * 4);
+        if (leader) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)      // +32 B along K inside the swizzle row = +2 in descriptor units
+            if (kk < ksteps)
+              tc_mma_bf16(d_tmem, DESC_HI | (uint64_t)(alo + 2 * kk), DESC_HI | (uint64_t)(blo + 2 * kk), idesc,
+                          (s | kk) != 0 ? 1u : 0u);
           tc_commit(empty0 + 8 * slot);
-          if (s == p.k_stages - 1) tc_commit(tfull0 + 8 * ab);
+          if (s == k_stages - 1) tc_commit(tfull0 + 8 * ab);
         }
         __syncwarp();
       }
@@ -367,15 +300,16 @@ cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-inline uint16_t f2bf(float f) {   // round-to-nearest-even, like __float2bfloat16_rn
+}  // namespace
+
+uint16_t f32_to_bf16_host(float f) {   // round-to-nearest-even, like __float2bfloat16_rn
   uint32_t u;
   memcpy(&u, &f, 4);
   if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
-
-}  // namespace
+static inline uint16_t f2bf(float f) { return f32_to_bf16_host(f); }
 
 // Choose XB (output pixels per GEMM row) for a layer.  Constraints: XB divides Wo; the run start must be
 // 16-byte aligned (XB*stride*Cin*2 % 16 == 0); N = XB*Cout in [16, 256], multiple of 16.
@@ -402,7 +336,13 @@ static int choose_xb(const ConvGeom& g) {
 int conv_bf16_prepare(ConvBf16Weights& wb, const std::vector<float>& wk, const std::vector<float>& bias,
                       const ConvGeom& g, const Tensor& in, const Tensor& out, std::vector<void*>& allocs,
                       std::string& err) {
-  (void)in; (void)out;
+  (void)out;
+  if (in.p && !getenv("UAHN_NO_TMA")) {
+    std::string terr;
+    const int rc = conv_tma_prepare(wb.tma, wk, bias, g, in, allocs, terr);
+    if (rc < 0) { err = terr; return rc; }
+    if (wb.tma.enabled) { wb.ready = 1; return 0; }
+  }
   const int xb = choose_xb(g);
   if (!xb) { err = "no valid Toeplitz factor"; return -1; }
   if (g.Cin % 8 && !(g.Cin == 2 && (xb * g.stride) % 4 == 0)) { err = "unsupported Cin"; return -1; }
@@ -453,7 +393,6 @@ int conv_bf16_prepare(ConvBf16Weights& wb, const std::vector<float>& wk, const s
 
 cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const float* bias, void* out,
                              const ConvGeom& g, cudaStream_t st) {
-  (void)bias;
   if (!wb.ready) return cudaErrorInvalidValue;
   static int num_sms = 0;
   if (!num_sms) {
@@ -461,6 +400,7 @@ cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const fl
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  if (wb.tma.enabled) return launch_conv_tma(wb.tma, bias, out, g, num_sms, st);
   IgemmParams p{};
   const int xb = wb.xb;
   p.in = (const uint8_t*)in;

@@ -7,7 +7,22 @@
 
 namespace uahn {
 
+// Shifted-window TMA plan (conv_bf16_tma.cu): the tile is a BW x BR patch of output pixel groups of one image;
+// every input row segment is loaded ONCE per tile by a 4-D tiled TMA (one "plane" per row parity and 64-element
+// chunk of the K run) and the KH kernel rows are MMAs whose A descriptor is shifted by whole patch rows.
+struct TmaPlan {
+  int enabled = 0;
+  alignas(64) unsigned char tmap[128];   // CUtensorMap over the haloed NHWC input (overlapping x windows)
+  int xb = 1, BW = 8, BR = 16, PX = 0, PY = 0;
+  int chunks = 1, run_elems = 0, n_planes = 0, n_slots = 0, slot_bytes = 0;
+  int plane_rows[8], plane_taps[8], plane_rho[8], plane_chunk[8];
+  void* b_image = nullptr;   // [KH*chunks][N][128 B]
+  float* bias_x = nullptr;
+  int n_total = 0;
+};
+
 struct ConvBf16Weights {
+  TmaPlan tma;
   void* b_image = nullptr;   // pre-swizzled B-operand stages in global memory
   int ready = 0;
   int xb = 1;                // output pixels per GEMM row (Toeplitz expansion along x)
@@ -22,6 +37,13 @@ struct ConvBf16Weights {
 int conv_bf16_prepare(ConvBf16Weights& wb, const std::vector<float>& wk, const std::vector<float>& bias,
                       const ConvGeom& g, const Tensor& in, const Tensor& out, std::vector<void*>& allocs,
                       std::string& err);
+// conv_bf16_tma.cu
+int conv_tma_prepare(TmaPlan& plan, const std::vector<float>& wk, const std::vector<float>& bias, const ConvGeom& g,
+                     const Tensor& in, std::vector<void*>& allocs, std::string& err);
+cudaError_t launch_conv_tma(const TmaPlan& plan, const float* bias, void* out, const ConvGeom& g, int num_sms,
+                            cudaStream_t st);
+uint16_t f32_to_bf16_host(float f);
+
 cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const float* bias, void* out,
                              const ConvGeom& g, cudaStream_t st);
 
