@@ -40,6 +40,12 @@ constexpr int MAX_SLOTS = 12;
 constexpr int MAX_OPS = 128;              // tcgen05.mma instructions per tile (KH taps x chunks x k-steps)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
+// Per-role cycle accounting (UAHN_TMA_DEBUG=1 prints it): compiled in only with -DUAHN_TMA_PROFILE=1.
+#ifndef UAHN_TMA_PROFILE
+#define UAHN_TMA_PROFILE 0
+#endif
+__device__ __forceinline__ long long prof_clock() { return UAHN_TMA_PROFILE ? clock64() : 0ll; }
+
 struct TmaConvParams {
   const uint8_t* b_image;
   const float* bias_x;
@@ -52,6 +58,7 @@ struct TmaConvParams {
   int out_pitch_y_b, out_col_step_b;
   long long out_origin_b;
   int n_total, act;
+  unsigned long long magic_tiles, magic_px;   // ceil(2^40 / tiles_per_img), ceil(2^40 / PX)
   unsigned long long* dbg;   // optional [grid][8] cycle counters (UAHN_TMA_DEBUG)
 };
 
@@ -118,21 +125,21 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
       for (int s = 0; s < p.b_stages; ++s)
         bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), p.b_image + (size_t)s * B_STAGE_BYTES, B_STAGE_BYTES, bres);
       int it = 0;
-      long long w_empty = 0, t_begin = clock64();
+      long long w_empty = 0, t_begin = prof_clock();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
         const int py = rem / p.PX, px = rem - py * p.PX;
         for (int pl = 0; pl < p.n_planes; ++pl, ++it) {
           const int slot = it % S;
-          const long long t0 = clock64();
+          const long long t0 = prof_clock();
           mbar_wait(empty0 + 8 * slot, ((it / S) & 1) ^ 1);
-          w_empty += clock64() - t0;
+          w_empty += prof_clock() - t0;
           mbar_arrive_expect_tx(full0 + 8 * slot, (uint32_t)(p.plane_rows[pl] * p.BW * 128));
           tma_load_4d(smem_u32(sA + (size_t)slot * p.slot_bytes), &tmap, p.plane_chunk[pl] * 64, px * p.BW,
                       p.stride * (py * p.BR) + p.plane_rho[pl], img, full0 + 8 * slot);
         }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = w_empty; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; }
+      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = w_empty; p.dbg[blockIdx.x * 8 + 1] = prof_clock() - t_begin; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -145,12 +152,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
     int it = 0, tcount = 0;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     mbar_wait(bres, 0);
-    long long w_tempty = 0, w_full = 0, t_begin = clock64();
+    long long w_tempty = 0, w_full = 0, t_begin = prof_clock();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int ab = tcount & 1;
-      long long t0 = clock64();
+      long long t0 = prof_clock();
       mbar_wait(tempty0 + 8 * ab, ((tcount >> 1) & 1) ^ 1);
-      w_tempty += clock64() - t0;
+      w_tempty += prof_clock() - t0;
       tc_fence_after();
       const uint32_t d_tmem = tmem_u + (uint32_t)(ab * BN);
       const bool leader = elect_one();
@@ -159,9 +166,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
         constexpr int dummy = 0; (void)dummy;
         const int rho = pl / CHUNKS, c = pl % CHUNKS;
         const int slot = it % S;
-        t0 = clock64();
+        t0 = prof_clock();
         mbar_wait(full0 + 8 * slot, (it / S) & 1);
-        w_full += clock64() - t0;
+        w_full += prof_clock() - t0;
         tc_fence_after();
         const uint32_t a16 = ((sA0 + (uint32_t)slot * slot_bytes) & 0x3FFFFu) >> 4;
         if (leader) {
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
       }
     }
     if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 8 + 2] = w_tempty; p.dbg[blockIdx.x * 8 + 3] = w_full; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      p.dbg[blockIdx.x * 8 + 2] = w_tempty; p.dbg[blockIdx.x * 8 + 3] = w_full; p.dbg[blockIdx.x * 8 + 4] = prof_clock() - t_begin;
     }
     tc_fence_before();
   } else {
@@ -198,15 +205,19 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
     constexpr int ROWS_PER_WARP = 32 / (EPI_WARPS / 4); // rows each warp stores after the quadrant's staging
     uint8_t* qOut = sOut + q * 32 * SROW;
     long long* qRow = sRowOff + q * 32;
+    float bias_r[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) bias_r[c] = sBias[cg * COLS + c];
     int tcount = 0;
-    long long w_tfull = 0, t_begin = clock64();
+    long long w_tfull = 0, t_begin = prof_clock(), c_ld = 0, c_math = 0, c_bar1 = 0, c_st = 0, c_bar2 = 0, c_pre = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const long long tp = prof_clock();
       const int ab = tcount & 1;
-      const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
-      const int py = rem / p.PX, px = rem - py * p.PX;
+      const int img = fast_div(tile, p.magic_tiles), rem = tile - img * tiles_per_img;
+      const int py = fast_div(rem, p.magic_px), px = rem - py * p.PX;
       if (cg == 0) {
         const int r = q * 32 + lane;
-        const int rr = r / p.BW, w = r - rr * p.BW;
+        const int rr = r >> 3, w = r & 7;               // BW = 8
         const int oy = py * p.BR + rr, oxb = px * p.BW + w;
         long long off = -1;
         if (rr < p.BR && oy < p.Ho && oxb < p.Wox)
@@ -214,9 +225,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
                 (long long)oxb * p.out_col_step_b;
         qRow[lane] = off;
       }
-      const long long t0 = clock64();
+      const long long t0 = prof_clock();
+      c_pre += t0 - tp;
       mbar_wait(tfull0 + 8 * ab, (tcount >> 1) & 1);
-      w_tfull += clock64() - t0;
+      const long long t1 = prof_clock();
+      w_tfull += t1 - t0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + cg * COLS);
       uint32_t r[COLS];
@@ -226,13 +239,15 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * ab);     // this warp's slice of the accumulator is in registers
+      const long long t2 = prof_clock();
+      c_ld += t2 - t1;
 #pragma unroll
       for (int c = 0; c < COLS / 16; ++c) {
         uint32_t packed[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float v0 = __uint_as_float(r[c * 16 + 2 * e]) + sBias[cg * COLS + c * 16 + 2 * e];
-          float v1 = __uint_as_float(r[c * 16 + 2 * e + 1]) + sBias[cg * COLS + c * 16 + 2 * e + 1];
+          float v0 = __uint_as_float(r[c * 16 + 2 * e]) + bias_r[c * 16 + 2 * e];
+          float v1 = __uint_as_float(r[c * 16 + 2 * e + 1]) + bias_r[c * 16 + 2 * e + 1];
           if (p.act) { v0 = fmaxf(v0, v0 * LRELU_SLOPE); v1 = fmaxf(v1, v1 * LRELU_SLOPE); }
           __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
           packed[e] = *reinterpret_cast<uint32_t*>(&h2);
@@ -242,7 +257,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
         o[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
       }
       // the 4 warps of a quadrant exchange column slices through shared memory: named barrier per quadrant
+      const long long t3 = prof_clock();
+      c_math += t3 - t2;
       asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "r"(32 * (EPI_WARPS / 4)) : "memory");
+      const long long t4 = prof_clock();
+      c_bar1 += t4 - t3;
       {
         const int rsub = lane / CPR, ch = lane % CPR;
 #pragma unroll
@@ -253,9 +272,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
           if (off >= 0) *reinterpret_cast<uint4*>(p.out + off + ch * 16) = v;
         }
       }
+      const long long t5 = prof_clock();
+      c_st += t5 - t4;
       asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "r"(32 * (EPI_WARPS / 4)) : "memory");
+      c_bar2 += prof_clock() - t5;
     }
-    if (p.dbg && warp == 2 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = w_tfull; p.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin; }
+    if (p.dbg && warp == 2 && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 5] = w_tfull; p.dbg[blockIdx.x * 8 + 6] = prof_clock() - t_begin;
+      unsigned long long* e = p.dbg + 8 * 1024 + blockIdx.x * 8;
+      e[0] = c_pre; e[1] = c_ld; e[2] = c_math; e[3] = c_bar1; e[4] = c_st; e[5] = c_bar2;
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -431,11 +457,13 @@ cudaError_t launch_conv_tma(const TmaPlan& plan, const float* bias, void* out, c
   p.act = g.act;
   const int tiles = p.n_img * p.PX * p.PY;
   const int grid = std::min(tiles, num_sms);
+  p.magic_tiles = ((1ull << 40) + p.PX * p.PY - 1) / (p.PX * p.PY);
+  p.magic_px = ((1ull << 40) + p.PX - 1) / p.PX;
   static unsigned long long* d_dbg = nullptr;
-  const bool debug = getenv("UAHN_TMA_DEBUG") != nullptr;
-  if (debug && !d_dbg) cudaMalloc(&d_dbg, 8 * 8 * 1024);
+  const bool debug = UAHN_TMA_PROFILE && getenv("UAHN_TMA_DEBUG") != nullptr;
+  if (debug && !d_dbg) cudaMalloc(&d_dbg, 2 * 8 * 8 * 1024);
   p.dbg = debug ? d_dbg : nullptr;
-  if (debug) cudaMemsetAsync(d_dbg, 0, 8 * 8 * 1024, st);
+  if (debug) cudaMemsetAsync(d_dbg, 0, 2 * 8 * 8 * 1024, st);
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(plan.tmap);
   const int ks0 = std::min(4, (plan.run_elems + 15) / 16);
   const int ks1 = plan.chunks > 1 ? std::min(4, (plan.run_elems - 64 + 15) / 16) : 0;
@@ -461,11 +489,15 @@ cudaError_t launch_conv_tma(const TmaPlan& plan, const float* bias, void* out, c
 #undef UAHN_TMA_CASE
   if (lerr != cudaSuccess) return lerr;
   if (debug) {
-    std::vector<unsigned long long> h(8 * grid);
+    std::vector<unsigned long long> h(8 * grid), h2(8 * grid);
     cudaStreamSynchronize(st);
     cudaMemcpy(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
-    double a[8] = {0};
-    for (int i = 0; i < grid; ++i) for (int j = 0; j < 8; ++j) a[j] += (double)h[i * 8 + j] / grid;
+    cudaMemcpy(h2.data(), d_dbg + 8 * 1024, h2.size() * 8, cudaMemcpyDeviceToHost);
+    double a[8] = {0}, b[8] = {0};
+    for (int i = 0; i < grid; ++i) for (int j = 0; j < 8; ++j) { a[j] += (double)h[i * 8 + j] / grid; b[j] += (double)h2[i * 8 + j] / grid; }
+    const double tl = (double)tiles / grid;
+    fprintf(stderr, "[uahn-tma]   epilogue warp 2 per tile: pre %.0f  wait_tfull %.0f  ld %.0f  math+sts %.0f  bar1 %.0f  store %.0f  bar2 %.0f\n",
+            b[0] / tl, a[5] / tl, b[1] / tl, b[2] / tl, b[3] / tl, b[4] / tl, b[5] / tl);
     fprintf(stderr, "[uahn-tma] Cin=%d Cout=%d out=%dx%d tiles/CTA=%.1f planes=%d | producer: wait_empty %.0f of %.0f | mma: wait_tempty %.0f wait_full %.0f of %.0f | epi(w2): wait_tfull %.0f of %.0f  (cycles, mean over CTAs)\n",
             g.Cin, g.Cout, g.Ho, g.Wo, (double)tiles / grid, p.n_planes, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
   }
