@@ -135,11 +135,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
           const bool gvalid = g < p.total_granules;            // the odd partner granule must be zero
           const uint8_t* src = p.in + (long long)ky * p.in_pitch_y_b + jj * 16;
           const uint32_t dst = smem_u32(sA + slot * A_STAGE_BYTES) + dst_off;
+          // rows past M (tail tile, batch-1 latency path) are never stored: leave their smem rows stale
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool ok = gvalid && ((rowok >> i) & 1u);
-            cp_async16(dst + i * 16 * 128, ok ? src + rowoff[i] : p.in, ok ? 16u : 0u);
-          }
+          for (int i = 0; i < 8; ++i)
+            if ((rowok >> i) & 1u) cp_async16(dst + i * 16 * 128, gvalid ? src + rowoff[i] : p.in, gvalid ? 16u : 0u);
         }
         cp_async_commit();
         if (it >= LAG) {

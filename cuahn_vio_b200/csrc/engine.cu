@@ -3,6 +3,7 @@
 // (reference model_to_trace.py:124-193, 258-282, 299-330); see DESIGN.md for the kernel map.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -118,6 +119,15 @@ struct uahn_handle {
   int img_counter = 0;
   double latest_time = -1.0;
   int last_n = 0;
+  // batch-1 latency path: the whole uahn_infer (H2D prior/rng, ~27 kernels, D2H results) is one CUDA graph per
+  // (ring slot, explicit masks?, error map?) combination, captured on the second call and replayed afterwards
+  cudaGraphExec_t graphs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t graph_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t* d_rng = nullptr;    // {seed, first_pair} read by the MC kernels during graph replay
+  uint64_t* h_rng = nullptr;    // pinned
+  float* h_prior = nullptr;     // pinned 8 floats
+  uint64_t infer_calls = 0;
+  bool use_graph = true;
   // per-category device timing (uahn_profile_*)
   struct ProfSpan { cudaEvent_t a, b; int cat; uint64_t launches; };
   bool prof_on = false;
@@ -341,7 +351,7 @@ int run_conv(uahn_handle* h, Layer& L, int n) {
 
 template <typename T>
 int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior, const uahn_rng* rng,
-            const uint8_t* d_masks, float* mean, float* cov, float* err) {
+            const uint8_t* d_masks, float* mean, float* cov, float* err, const uint64_t* rng_dev = nullptr) {
   cudaStream_t st = h->stream;
   const int variant = h->cfg.variant;
   const float* Hcur = nullptr;
@@ -381,7 +391,7 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
   const T* feat = (const T*)B4.layers.back().out.p;
   const uint64_t seed = rng ? rng->seed : 0, first = rng ? rng->first_pair_index : 0;
   h->prof_begin(3);
-  LAUNCH(launch_mc_expand<T>(n, feat, (T*)h->mcA, d_masks, seed, first, st));
+  LAUNCH(launch_mc_expand<T>(n, feat, (T*)h->mcA, d_masks, seed, first, rng_dev, st));
   h->prof_end();
   h->prof_begin(2);
   for (int head = 0; head < 2; ++head) {
@@ -397,7 +407,7 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
   h->prof_end();
   const bool want_err = h->cfg.show_error && err;
   h->prof_begin(3);
-  LAUNCH(launch_mc_final<T>(n, (const T*)h->hid, h->W2m, h->b2m, h->W2u, h->b2u, Hcur, d_masks, seed, first, mean, cov,
+  LAUNCH(launch_mc_final<T>(n, (const T*)h->hid, h->W2m, h->b2m, h->W2u, h->b2u, Hcur, d_masks, seed, first, rng_dev, mean, cov,
                             h->cfg.show_error ? h->Htot : nullptr, h->mc_mean, h->mc_logvar, st));
   h->prof_end();
   if (want_err) {
@@ -410,10 +420,11 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
 }
 
 int forward_any(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior,
-                const uahn_rng* rng, const uint8_t* d_masks, float* mean, float* cov, float* err) {
+                const uahn_rng* rng, const uint8_t* d_masks, float* mean, float* cov, float* err,
+                const uint64_t* rng_dev = nullptr) {
   if (n <= 0 || n > h->cap) return h->fail(UAHN_ERR_INVALID, "n=%d outside [1, max_batch=%d]", n, h->cap);
-  return h->bf16 ? forward<__nv_bfloat16>(h, n, prev, curr, prior, rng, d_masks, mean, cov, err)
-                 : forward<float>(h, n, prev, curr, prior, rng, d_masks, mean, cov, err);
+  return h->bf16 ? forward<__nv_bfloat16>(h, n, prev, curr, prior, rng, d_masks, mean, cov, err, rng_dev)
+                 : forward<float>(h, n, prev, curr, prior, rng, d_masks, mean, cov, err, rng_dev);
 }
 
 }  // namespace
@@ -495,7 +506,11 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
   if ((rc = dev_alloc(h, &h->d_cov, cap * 64))) return bail(rc);
   if (cfg->show_error && (rc = dev_alloc(h, &h->d_err, cap * IMG_PIXELS))) return bail(rc);
   if ((rc = dev_alloc(h, &h->d_ring, (size_t)2 * IMG_PIXELS))) return bail(rc);
-  if ((e = cudaMallocHost((void**)&h->h_img, IMG_PIXELS)) != cudaSuccess ||
+  if ((rc = dev_alloc(h, &h->d_rng, 2))) return bail(rc);
+  h->use_graph = getenv("UAHN_NO_GRAPH") == nullptr;
+  if ((e = cudaMallocHost((void**)&h->h_rng, 16)) != cudaSuccess ||
+      (e = cudaMallocHost((void**)&h->h_prior, 32)) != cudaSuccess ||
+      (e = cudaMallocHost((void**)&h->h_img, IMG_PIXELS)) != cudaSuccess ||
       (e = cudaMallocHost((void**)&h->h_out, (72 + IMG_PIXELS) * sizeof(float))) != cudaSuccess) {
     h->fail(UAHN_ERR_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e));
     return bail(UAHN_ERR_CUDA);
@@ -514,6 +529,9 @@ void uahn_destroy(uahn_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   for (auto& sp : h->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
+  for (cudaGraphExec_t g : h->graphs) if (g) cudaGraphExecDestroy(g);
+  if (h->h_rng) cudaFreeHost(h->h_rng);
+  if (h->h_prior) cudaFreeHost(h->h_prior);
   if (h->h_img) cudaFreeHost(h->h_img);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -595,10 +613,10 @@ int uahn_infer(uahn_handle* h, const double* prior_px, const uahn_rng* rng, doub
   const bool need_prior = h->cfg.variant != UAHN_VARIANT_FULL;
   if (need_prior) {
     if (!prior_px) return h->fail(UAHN_ERR_INVALID, "this variant needs a prior");
-    float pf[8];
-    for (int i = 0; i < 8; ++i) pf[i] = (float)prior_px[i];                 // HomographyNet.cpp:160-165 (.toType(kFloat))
-    CK(cudaMemcpyAsync(h->d_prior, pf, sizeof(pf), cudaMemcpyHostToDevice, st));   // pageable: staged before return
+    for (int i = 0; i < 8; ++i) h->h_prior[i] = (float)prior_px[i];        // HomographyNet.cpp:160-165 (.toType(kFloat))
   }
+  h->h_rng[0] = rng ? rng->seed : 0;
+  h->h_rng[1] = rng ? rng->first_pair_index : 0;
   const uint8_t* dm = nullptr;
   if (rng && rng->keep_masks) {
     if (!h->d_masks) {
@@ -610,12 +628,43 @@ int uahn_infer(uahn_handle* h, const double* prior_px, const uahn_rng* rng, doub
   }
   const uint8_t* curr = h->d_ring + (size_t)h->ring_curr * IMG_PIXELS;
   const uint8_t* prev = h->d_ring + (size_t)(h->ring_curr ^ 1) * IMG_PIXELS;
-  int rc = forward_any(h, 1, prev, curr, need_prior ? h->d_prior : nullptr, rng, dm, h->d_mean, h->d_cov,
-                       err_map ? h->d_err : nullptr);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(h->h_out, h->d_mean, 8 * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(h->h_out + 8, h->d_cov, 64 * 4, cudaMemcpyDeviceToHost, st));
-  if (err_map) CK(cudaMemcpyAsync(h->h_out + 72, h->d_err, (size_t)IMG_PIXELS * 4, cudaMemcpyDeviceToHost, st));
+  // everything between the host buffers: prior + rng H2D, the forward, results D2H
+  auto enqueue = [&]() -> int {
+    if (need_prior) CK(cudaMemcpyAsync(h->d_prior, h->h_prior, 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_rng, h->h_rng, 16, cudaMemcpyHostToDevice, st));
+    int rc = forward_any(h, 1, prev, curr, need_prior ? h->d_prior : nullptr, rng, dm, h->d_mean, h->d_cov,
+                         err_map ? h->d_err : nullptr, h->d_rng);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->h_out, h->d_mean, 8 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_out + 8, h->d_cov, 64 * 4, cudaMemcpyDeviceToHost, st));
+    if (err_map) CK(cudaMemcpyAsync(h->h_out + 72, h->d_err, (size_t)IMG_PIXELS * 4, cudaMemcpyDeviceToHost, st));
+    return UAHN_OK;
+  };
+  const int key = h->ring_curr | (dm ? 2 : 0) | (err_map ? 4 : 0);
+  const bool graphable = h->use_graph && !h->prof_on && h->infer_calls >= 2;   // first calls run eagerly (lazy attributes)
+  ++h->infer_calls;
+  if (graphable && !h->graphs[key]) {
+    const uint64_t l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue();
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return h->fail(UAHN_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&h->graphs[key], graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { h->graphs[key] = nullptr; return h->fail(UAHN_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce)); }
+    h->graph_launches[key] = h->launches - l0;
+    h->launches = l0;       // capture enqueued nothing; replays are counted below
+  }
+  if (graphable) {
+    CK(cudaGraphLaunch(h->graphs[key], st));
+    h->launches += h->graph_launches[key];
+    h->last_n = 1;
+  } else {
+    int rc = enqueue();
+    if (rc) return rc;
+  }
   CK(cudaStreamSynchronize(st));
   for (int i = 0; i < 8; ++i) mean8[i] = h->h_out[i];
   for (int i = 0; i < 64; ++i) cov64[i] = h->h_out[8 + i];

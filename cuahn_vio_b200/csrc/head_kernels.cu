@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(256) fc8_dlt_kernel(const T* __restrict__ feat
 template <typename T>
 __global__ void __launch_bounds__(256) mc_expand_kernel(const T* __restrict__ feat, T* __restrict__ A, int n,
                                                          const uint8_t* __restrict__ keep_masks, uint64_t seed,
-                                                         uint64_t first_pair) {
+                                                         uint64_t first_pair, const uint64_t* __restrict__ rng_dev) {
+  if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }   // graph replay: values live in device memory
   const int pair = blockIdx.x, head = blockIdx.y;
   const T* f = feat + (size_t)pair * FC_IN;
   T* a = A + ((size_t)head * n + pair) * MC * FC_IN;
@@ -224,7 +225,9 @@ __global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid
                                                         const float* __restrict__ b2m, const float* __restrict__ W2u,
                                                         const float* __restrict__ b2u, const float* __restrict__ Hpart1,
                                                         const uint8_t* __restrict__ keep_masks, uint64_t seed,
-                                                        uint64_t first_pair, HeadOut o) {
+                                                        uint64_t first_pair, const uint64_t* __restrict__ rng_dev,
+                                                        HeadOut o) {
+  if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }
   __shared__ float w2[2][8][FC_HID];
   __shared__ float outv[2][MC][8];
   __shared__ float mu_s[8], var_s[8];
@@ -359,29 +362,30 @@ template cudaError_t launch_fc8_dlt<__nv_bfloat16>(int, const __nv_bfloat16*, co
 
 template <typename T>
 cudaError_t launch_mc_expand(int n, const T* feat, T* A, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,
-                             cudaStream_t st) {
-  mc_expand_kernel<T><<<dim3(n, 2), 256, 0, st>>>(feat, A, n, keep_masks, seed, first_pair);
+                             const uint64_t* rng_dev, cudaStream_t st) {
+  mc_expand_kernel<T><<<dim3(n, 2), 256, 0, st>>>(feat, A, n, keep_masks, seed, first_pair, rng_dev);
   return cudaGetLastError();
 }
 template cudaError_t launch_mc_expand<float>(int, const float*, float*, const uint8_t*, uint64_t, uint64_t,
-                                             cudaStream_t);
+                                             const uint64_t*, cudaStream_t);
 template cudaError_t launch_mc_expand<__nv_bfloat16>(int, const __nv_bfloat16*, __nv_bfloat16*, const uint8_t*,
-                                                     uint64_t, uint64_t, cudaStream_t);
+                                                     uint64_t, uint64_t, const uint64_t*, cudaStream_t);
 
 template <typename T>
 cudaError_t launch_mc_final(int n, const T* hid, const float* W2m, const float* b2m, const float* W2u,
                             const float* b2u, const float* Hpart1, const uint8_t* keep_masks, uint64_t seed,
-                            uint64_t first_pair, float* mean, float* cov, float* Htot, float* mc_mean,
-                            float* mc_logvar, cudaStream_t st) {
+                            uint64_t first_pair, const uint64_t* rng_dev, float* mean, float* cov, float* Htot,
+                            float* mc_mean, float* mc_logvar, cudaStream_t st) {
   HeadOut o{mean, cov, Htot, mc_mean, mc_logvar};
-  mc_final_kernel<T><<<n, 256, 0, st>>>(hid, n, W2m, b2m, W2u, b2u, Hpart1, keep_masks, seed, first_pair, o);
+  mc_final_kernel<T><<<n, 256, 0, st>>>(hid, n, W2m, b2m, W2u, b2u, Hpart1, keep_masks, seed, first_pair, rng_dev, o);
   return cudaGetLastError();
 }
 template cudaError_t launch_mc_final<float>(int, const float*, const float*, const float*, const float*, const float*,
-                                            const float*, const uint8_t*, uint64_t, uint64_t, float*, float*, float*,
-                                            float*, float*, cudaStream_t);
+                                            const float*, const uint8_t*, uint64_t, uint64_t, const uint64_t*, float*,
+                                            float*, float*, float*, float*, cudaStream_t);
 template cudaError_t launch_mc_final<__nv_bfloat16>(int, const __nv_bfloat16*, const float*, const float*,
                                                     const float*, const float*, const float*, const uint8_t*, uint64_t,
-                                                    uint64_t, float*, float*, float*, float*, float*, cudaStream_t);
+                                                    uint64_t, const uint64_t*, float*, float*, float*, float*, float*,
+                                                    cudaStream_t);
 
 }  // namespace uahn

@@ -192,6 +192,24 @@ def test_streaming_call_surface(api, wfile):
         m2, _, _ = net.infer(prior[1].reshape(8), seed=9, pair_index=1)
         mb2, _, _ = net.infer_batch(frames[1][None], frames[2][None], prior[1:2], seed=9, first_pair=1)
         assert np.array_equal(m2.astype(np.float32), mb2[0])
+    # CUDA-graph replay (third call onwards) must reproduce the eager results and honour per-call seeds
+    for precision in ("fp32", "bf16"):
+        with api.Uahn(wfile, "prior3", show_error=True, precision=precision, max_batch=1) as net:
+            net.load_image(frames[0], 1.0)
+            net.load_image(frames[1], 2.0)
+            ref = [net.infer(prior[0].reshape(8), seed=3, pair_index=i, want_error=(i % 2 == 0)) for i in range(2)]   # eager
+            l0 = net.launch_count
+            again = [net.infer(prior[0].reshape(8), seed=3, pair_index=i, want_error=(i % 2 == 0)) for i in range(2)]  # graphs
+            assert net.launch_count - l0 >= 2 * 20            # replays are counted as the kernels they contain
+            for (m0, c0, e0), (m1, c1, e1) in zip(ref, again):
+                assert np.array_equal(m0, m1) and np.array_equal(c0, c1)
+                assert (e0 is None and e1 is None) or np.array_equal(e0, e1)
+            m5, _, _ = net.infer(prior[0].reshape(8), seed=3, pair_index=5)
+            assert not np.array_equal(m5, ref[0][0])
+            net.load_image(frames[2], 3.0)                     # other ring slot -> its own graph
+            mg, _, _ = net.infer(prior[1].reshape(8), seed=3, pair_index=1)
+            mb, _, _ = net.infer_batch(frames[1][None], frames[2][None], prior[1:2], seed=3, first_pair=1)
+            assert np.array_equal(mg.astype(np.float32), mb[0])
     hn = api.HomographyNet(wfile, use_prior=True, precision="fp32")
     hn.load_current_img(frames[0], 0.1)
     hn.network_inference(prior[0].reshape(8), 0)     # prints, leaves outputs untouched
