@@ -29,7 +29,6 @@ namespace {
 constexpr int BM = 128;                 // UMMA M
 constexpr int A_STAGE_BYTES = BM * 128; // 128 rows x 64 bf16 (one 128 B swizzle row each)
 constexpr int IG_THREADS = 320;         // warps 0-3 gather A, 4 MMA, 5 B loader, 6-9 epilogue
-constexpr int LAG = 2;                  // cp.async groups in flight per gather thread
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct IgemmParams {
@@ -140,19 +139,14 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
           for (int i = 0; i < 8; ++i)
             if ((rowok >> i) & 1u) cp_async16(dst + i * 16 * 128, gvalid ? src + rowoff[i] : p.in, gvalid ? 16u : 0u);
         }
-        cp_async_commit();
-        if (it >= LAG) {
-          cp_async_wait<LAG>();
-          fence_proxy_async();
-          mbar_arrive(full0 + 8 * ((it - LAG) % STAGES));
-        }
+        // the hardware arrives on the stage's full barrier when this thread's copies have landed (no wait here,
+        // same producer protocol as CUTLASS's sm100 cp.async + UMMA mainloop)
+        cp_async_mbar_arrive_noinc(full0 + 8 * slot);
         jj += 8;
         while (jj >= p.run_granules) { jj -= p.run_granules; ++ky; }
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int s = max(0, it - LAG); s < it; ++s) mbar_arrive(full0 + 8 * (s % STAGES));
+    cp_async_wait_all();
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     // The whole warp runs the (warp-uniform) loop control; only the tcgen05 instructions are predicated on the

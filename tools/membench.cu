@@ -131,6 +131,36 @@ __global__ void __launch_bounds__(THREADS) k_ldgsts(const uint8_t* src, size_t s
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---------------- (c') cp.async 16 B in the conv-gather pattern: 8 lanes per 128-byte row, rows ROW_STRIDE apart,
+// zero-fill form, swizzled destination, fence.proxy.async + mbarrier arrive per stage ----------------
+template <int LAG, bool ZFILL, bool FENCE>
+__global__ void __launch_bounds__(128) k_gather(const uint8_t* src, size_t src_bytes, int row_stride, int per_cta) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  constexpr int STAGE = 16384, S = LAG + 1;
+  const int tid = threadIdx.x, j = tid & 7, rb = tid >> 3;
+  if (tid == 0) mbar_init(smem_u32(&bar), 128);
+  __syncthreads();
+  const uint32_t dst_off = (uint32_t)rb * 128 + (uint32_t)((j ^ (rb & 7)) << 4);
+  for (int i = 0; i < per_cta; ++i) {
+    const size_t tile = ((size_t)(blockIdx.x + (size_t)i * gridDim.x) * 128 * row_stride) % (src_bytes - (size_t)129 * row_stride);
+    const uint32_t dst = smem_u32(smem + (i % S) * STAGE) + dst_off;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint8_t* p = src + tile + (size_t)(rb + 16 * r) * row_stride + j * 16;
+      if (ZFILL) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + r * 16 * 128), "l"(p), "r"(16u) : "memory");
+      else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * 16 * 128), "l"(p) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(LAG) : "memory");
+    if (FENCE) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(smem_u32(&bar));
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------- (d) LDG.128 -> STS.128, UNROLL loads in flight per thread ----------------
 template <int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS) k_ldg_sts(const uint4* src, size_t src_vecs, int per_cta) {
@@ -250,6 +280,27 @@ int main() {
       run(k_ldgsts<128, 5>, 128, 5, "cp.async 16B, 128 thr, 6 stages in flight");
       run(k_ldgsts<256, 5>, 256, 5, "cp.async 16B, 256 thr, 6 stages in flight");
       run(k_ldgsts<512, 5>, 512, 5, "cp.async 16B, 512 thr, 6 stages in flight");
+    }
+    // (c') conv-gather pattern
+    {
+      const int per = 400;
+      auto run = [&](auto kern, int lag, int stride, const char* nm) {
+        const size_t smem = (size_t)(lag + 1) * 16384;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<sms, 128, smem>>>(d, foot, stride, 20);
+        cudaEventRecord(e0);
+        kern<<<sms, 128, smem>>>(d, foot, stride, per);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        report(nm, (double)sms * per * 16384, ms);
+      };
+      run(k_gather<2, false, false>, 2, 128, "gather rows@128B (contiguous), lag 2");
+      run(k_gather<2, false, false>, 2, 512, "gather rows@512B, lag 2");
+      run(k_gather<2, true, false>, 2, 512, "gather rows@512B, zfill form, lag 2");
+      run(k_gather<2, true, true>, 2, 512, "gather rows@512B, zfill + fence + mbar, lag 2");
+      run(k_gather<5, true, true>, 5, 512, "gather rows@512B, zfill + fence + mbar, lag 5");
+      run(k_gather<2, true, true>, 2, 576, "gather rows@576B (64B-misaligned rows), full, lag 2");
     }
     // (d) LDG + STS
     {
