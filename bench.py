@@ -251,12 +251,20 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(W):
-        step(i)
-    barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks:
         clocks.start()
+    for i in range(W):
+        step(i)
+    # keep the GPU under the same load for ~0.6 s before the timed region so the 200 ms clock sampler sees it
+    t_load = time.perf_counter()
+    j = 0
+    while time.perf_counter() - t_load < 0.6:
+        step(j)
+        j += 1
+        if j % 8 == 0:
+            torch.cuda.synchronize()
+    barrier()
     net.profile_enable(True)
     l0 = net.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -312,6 +320,12 @@ def run_ours(args):
         return
 
     peaks = measured_peaks()
+    # DRAM traffic of the conv group from the committed ncu --set full capture of this workload (per pair)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if os.path.exists(tpath) and args.precision == "bf16":
+        tj = json.load(open(tpath))
+        traffic = tj["conv_group_dram_bytes_per_step"] / tj["pairs"] * B
     conv_ms_per_step = prof_ms[1] / K
     tensor_flops = 2.0 * CONV_MACS * B
     achieved = tensor_flops / (conv_ms_per_step * 1e-3) / 1e12 if conv_ms_per_step > 0 else 0.0
@@ -332,7 +346,10 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "traffic_note": "dram__bytes_read+write summed over the 17 conv launches of one step (ncu --set full, "
+                                     "profiles/r01_ncu_conv_layers_b1024.csv); the group is HBM-bound: see hbm_frac_conv_group",
+                     "hbm_frac_conv_group": (traffic / (conv_ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic and conv_ms_per_step > 0 else None,
                      "kernel": "conv implicit-GEMM (17 launches per step: blocks 2,3,4)",
                      "algorithmic_flops_per_launch_group": tensor_flops, "ms_per_step": conv_ms_per_step,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})"},
