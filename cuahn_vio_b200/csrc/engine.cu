@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <string>
@@ -79,6 +80,7 @@ struct Layer {
 struct Block {
   int id = 0, pool = 1;
   bool active = false;
+  int chunk_cap = 0;        // pairs held by x and layers[0].out (L2-resident chunking of the block front)
   Tensor x;                 // 2-channel conv input
   std::vector<Layer> layers;
   float* W8 = nullptr;      // [8][5120] permuted to NHWC feature order (blocks 1-3)
@@ -128,6 +130,10 @@ struct uahn_handle {
   float* h_prior = nullptr;     // pinned 8 floats
   uint64_t infer_calls = 0;
   bool use_graph = true;
+  // pairs per chunk of the block-3/4 fronts (UAHN_L2_CHUNK).  Measured on B200 at 1024 pairs/step: chunks of
+  // 16/32/64 pairs run the step 2.4x/1.65x/1.3x SLOWER than unchunked (launch + pipeline fill/drain of ~190 extra
+  // launches outweigh the saved HBM round trip), so chunking is off by default.
+  int l2_chunk = 1 << 30;
   // per-category device timing (uahn_profile_*)
   struct ProfSpan { cudaEvent_t a, b; int cat; uint64_t launches; };
   bool prof_on = false;
@@ -257,7 +263,11 @@ int build_block(uahn_handle* h, const std::map<std::string, HostTensor>& w, int 
   B.id = id; B.pool = pool; B.active = true;
   const char* pre = id == 4 ? P4 : P1;
   int H = IMG_H / pool, W = IMG_W / pool;
-  int rc = make_tensor(h, B.x, h->cap, H, W, 2, (specs[0].k - 1) / 2);
+  // Blocks 3 and 4: the warp output and the first conv's output are the largest activations (0.7 / 1.4 MB per
+  // pair).  They live in chunk-sized buffers that are re-used for every chunk of `l2_chunk` pairs, so the
+  // warp -> conv0 -> conv1 chain of a chunk runs out of L2 and those bytes never round-trip HBM.
+  B.chunk_cap = (id >= 3) ? std::min(h->cap, h->l2_chunk) : h->cap;
+  int rc = make_tensor(h, B.x, B.chunk_cap, H, W, 2, (specs[0].k - 1) / 2);
   if (rc) return rc;
   Tensor cur = B.x;
   std::string err;
@@ -270,7 +280,7 @@ int build_block(uahn_handle* h, const std::map<std::string, HostTensor>& w, int 
     L.Wo = (W + 2 * p - L.spec.k) / L.spec.stride + 1;
     L.in = cur;
     const int next_pad = i + 1 < nl ? (specs[i + 1].k - 1) / 2 : 0;
-    rc = make_tensor(h, L.out, h->cap, L.Ho, L.Wo, L.spec.cout, next_pad);
+    rc = make_tensor(h, L.out, i == 0 ? B.chunk_cap : h->cap, L.Ho, L.Wo, L.spec.cout, next_pad);
     if (rc) return rc;
     const std::string key = std::string(pre) + L.spec.name + ".0.";
     const HostTensor* wt = find(w, key + "weight", {L.spec.cout, L.spec.cin, L.spec.k, L.spec.k}, err);
@@ -339,13 +349,39 @@ int build_head(uahn_handle* h, const std::map<std::string, HostTensor>& w) {
 }
 
 template <typename T>
-int run_conv(uahn_handle* h, Layer& L, int n) {
+int run_conv(uahn_handle* h, Layer& L, int n, size_t out_img0 = 0) {
   ConvGeom g = make_geom(L, n);
+  T* out = (T*)L.out.p + out_img0 * (size_t)L.out.pitch_n;     // first output image (chunked block fronts)
   if constexpr (sizeof(T) == 4) {
-    LAUNCH(launch_conv_f32((const float*)L.in.p, L.w_f32, L.bias, (float*)L.out.p, g, h->stream));
+    LAUNCH(launch_conv_f32((const float*)L.in.p, L.w_f32, L.bias, (float*)out, g, h->stream));
   } else {
-    LAUNCH(launch_conv_bf16(L.wb, L.in.p, L.bias, L.out.p, g, h->stream));
+    LAUNCH(launch_conv_bf16(L.wb, L.in.p, L.bias, out, g, h->stream));
   }
+  return UAHN_OK;
+}
+
+// warp + concat + pool -> conv stack of one cascade block.  The front (warp, conv 0, conv 1) runs per L2-sized chunk.
+template <typename T>
+int run_block(uahn_handle* h, Block& B, int n, const uint8_t* prev, const uint8_t* curr, const float* Hcur) {
+  cudaStream_t st = h->stream;
+  int rc;
+  const int CH = B.chunk_cap;
+  const size_t nl = B.layers.size();
+  for (int c0 = 0; c0 < n; c0 += CH) {
+    const int nc = std::min(CH, n - c0);
+    h->prof_begin(0);
+    LAUNCH(launch_warp_concat_pool<T>(prev + (size_t)c0 * IMG_PIXELS, curr + (size_t)c0 * IMG_PIXELS,
+                                      Hcur ? Hcur + (size_t)c0 * 9 : nullptr, B.x, B.pool, nc, st));
+    h->prof_end();
+    h->prof_begin(1);
+    if ((rc = run_conv<T>(h, B.layers[0], nc))) return rc;
+    if (CH < h->cap && nl > 1 && (rc = run_conv<T>(h, B.layers[1], nc, (size_t)c0))) return rc;
+    h->prof_end();
+  }
+  h->prof_begin(1);
+  for (size_t i = (CH < h->cap ? 2 : 1); i < nl; ++i)
+    if ((rc = run_conv<T>(h, B.layers[i], n))) return rc;
+  h->prof_end();
   return UAHN_OK;
 }
 
@@ -367,13 +403,7 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
     Block& B = h->blocks[b];
     if (!B.active) continue;
     // block 1 sees the raw current image (model_to_trace.py:138-139); blocks 2,3 the warped one (:154,172)
-    h->prof_begin(0);
-    LAUNCH(launch_warp_concat_pool<T>(prev, curr, b == 1 ? nullptr : Hcur, B.x, B.pool, n, st));
-    h->prof_end();
-    h->prof_begin(1);
-    for (Layer& L : B.layers)
-      if ((rc = run_conv<T>(h, L, n))) return rc;
-    h->prof_end();
+    if ((rc = run_block<T>(h, B, n, prev, curr, b == 1 ? nullptr : Hcur))) return rc;
     h->prof_begin(3);
     LAUNCH(launch_fc8_dlt<T>(n, (const T*)B.layers.back().out.p, B.W8, B.b8, b == 1 ? nullptr : Hcur, h->Hb[b],
                              h->dblk[b], st));
@@ -381,13 +411,7 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
     Hcur = h->Hb[b];
   }
   Block& B4 = h->blocks[4];
-  h->prof_begin(0);
-  LAUNCH(launch_warp_concat_pool<T>(prev, curr, Hcur, B4.x, 1, n, st));     // model_to_trace.py:261-263
-  h->prof_end();
-  h->prof_begin(1);
-  for (Layer& L : B4.layers)
-    if ((rc = run_conv<T>(h, L, n))) return rc;
-  h->prof_end();
+  if ((rc = run_block<T>(h, B4, n, prev, curr, Hcur))) return rc;             // model_to_trace.py:261-263
   const T* feat = (const T*)B4.layers.back().out.p;
   const uint64_t seed = rng ? rng->seed : 0, first = rng ? rng->first_pair_index : 0;
   h->prof_begin(3);
@@ -442,6 +466,7 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
   h->cfg = *cfg;
   h->cap = cfg->max_batch;
   h->bf16 = cfg->precision == UAHN_PRECISION_BF16;
+  if (const char* e = getenv("UAHN_L2_CHUNK")) h->l2_chunk = std::max(1, atoi(e));
   h->es = h->bf16 ? 2 : 4;
   auto bail = [&](int rc) {
     g_create_error = h->last_error;
@@ -827,6 +852,7 @@ long uahn_debug_read(uahn_handle* h, const char* what, float* out, size_t capaci
         if (h->blocks[b].active && w.substr(4) == L.spec.name) t = &L.out;
   }
   if (!t) return h->fail(UAHN_ERR_INVALID, "unknown debug tensor '%s'", what);
+  if (n > t->N) return h->fail(UAHN_ERR_STATE, "'%s' is chunk-resident (%d pairs); rerun with n <= %d to read it", what, t->N, t->N);
   const size_t count = (size_t)n * t->C * t->H * t->W;
   if (count > capacity) return h->fail(UAHN_ERR_INVALID, "capacity too small (%zu needed)", count);
   std::vector<uint8_t> raw((size_t)n * t->pitch_n * h->es);
