@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "uahn_create", "uahn_destroy", "uahn_last_error", "uahn_load_image", "uahn_infer", "uahn_infer_batch",
     "uahn_infer_batch_device", "uahn_synchronize", "uahn_stream", "uahn_launch_count",
     "uahn_latest_inference_time", "uahn_image_count", "uahn_philox_keep_masks", "uahn_stage_dlt",
-    "uahn_stage_warp", "uahn_debug_read", "uahn_profile_enable", "uahn_profile_read", "uahn_stage_conv",
+    "uahn_stage_warp", "uahn_debug_read", "uahn_profile_enable", "uahn_profile_read", "uahn_stage_conv", "uahn_submit_batch", "uahn_wait",
 ]
 
 
@@ -62,6 +62,10 @@ def load_library(path: str | None = None):
     for f in (lib.uahn_infer_batch, lib.uahn_infer_batch_device):
         f.argtypes = [vp, i, vp, vp, vp, C.POINTER(_Rng), vp, vp, vp]
         f.restype = i
+    lib.uahn_submit_batch.argtypes = [vp, i, vp, vp, vp, C.POINTER(_Rng), vp, vp]
+    lib.uahn_submit_batch.restype = i
+    lib.uahn_wait.argtypes = [vp]
+    lib.uahn_wait.restype = i
     lib.uahn_synchronize.argtypes = [vp]
     lib.uahn_synchronize.restype = i
     lib.uahn_stream.argtypes = [vp]
@@ -186,6 +190,15 @@ class Uahn:
         rng = _Rng(seed, first_pair, None)
         f = self._lib.uahn_infer_batch_device if device else self._lib.uahn_infer_batch
         self._check(f(self._h, n, _ptr(prev), _ptr(curr), _ptr(prior), C.byref(rng), _ptr(mean), _ptr(cov), _ptr(err)))
+
+    def submit_batch_ptrs(self, n, prev, curr, prior, mean, cov, seed=0, first_pair=0):
+        """Pipelined host-buffer submission (raw addresses of pinned host memory); pair with wait()."""
+        rng = _Rng(seed, first_pair, None)
+        self._check(self._lib.uahn_submit_batch(self._h, n, _ptr(prev), _ptr(curr), _ptr(prior), C.byref(rng), _ptr(mean),
+                                                _ptr(cov)))
+
+    def wait(self):
+        self._check(self._lib.uahn_wait(self._h))
 
     def synchronize(self):
         self._check(self._lib.uahn_synchronize(self._h))

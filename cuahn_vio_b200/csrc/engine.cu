@@ -134,6 +134,12 @@ struct uahn_handle {
   // 16/32/64 pairs run the step 2.4x/1.65x/1.3x SLOWER than unchunked (launch + pipeline fill/drain of ~190 extra
   // launches outweigh the saved HBM round trip), so chunking is off by default.
   int l2_chunk = 1 << 30;
+  // pipelined submissions (uahn_submit_batch): copy stream + second staging set
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  uint8_t *s_prev[2] = {nullptr, nullptr}, *s_curr[2] = {nullptr, nullptr};
+  float *s_prior[2] = {nullptr, nullptr}, *s_mean[2] = {nullptr, nullptr}, *s_cov[2] = {nullptr, nullptr};
+  uint64_t submit_count = 0;
   // per-category device timing (uahn_profile_*)
   struct ProfSpan { cudaEvent_t a, b; int cat; uint64_t launches; };
   bool prof_on = false;
@@ -554,6 +560,8 @@ void uahn_destroy(uahn_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   for (auto& sp : h->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
   for (cudaGraphExec_t g : h->graphs) if (g) cudaGraphExecDestroy(g);
   if (h->h_rng) cudaFreeHost(h->h_rng);
   if (h->h_prior) cudaFreeHost(h->h_prior);
@@ -609,6 +617,55 @@ int uahn_infer_batch(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* 
   CK(cudaMemcpyAsync(cov, h->d_cov, (size_t)n * 64 * 4, cudaMemcpyDeviceToHost, st));
   if (err) CK(cudaMemcpyAsync(err, h->d_err, (size_t)n * IMG_PIXELS * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return UAHN_OK;
+}
+
+int uahn_submit_batch(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior,
+                      const uahn_rng* rng, float* mean, float* cov) {
+  if (!h) return UAHN_ERR_INVALID;
+  if (!prev || !curr || !mean || !cov) return h->fail(UAHN_ERR_INVALID, "null buffer");
+  if (n <= 0 || n > h->cap) return h->fail(UAHN_ERR_INVALID, "n=%d outside [1, max_batch=%d]", n, h->cap);
+  if (rng && rng->keep_masks) return h->fail(UAHN_ERR_UNSUPPORTED, "explicit masks are not supported by uahn_submit_batch");
+  if (h->cfg.variant != UAHN_VARIANT_FULL && !prior) return h->fail(UAHN_ERR_INVALID, "this variant needs a prior");
+  CK(cudaSetDevice(h->cfg.device));
+  if (!h->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    h->s_prev[0] = h->d_prev; h->s_curr[0] = h->d_curr; h->s_prior[0] = h->d_prior;
+    h->s_mean[0] = h->d_mean; h->s_cov[0] = h->d_cov;
+    int rc;
+    if ((rc = dev_alloc(h, &h->s_prev[1], (size_t)h->cap * IMG_PIXELS))) return rc;
+    if ((rc = dev_alloc(h, &h->s_curr[1], (size_t)h->cap * IMG_PIXELS))) return rc;
+    if ((rc = dev_alloc(h, &h->s_prior[1], (size_t)h->cap * 8))) return rc;
+    if ((rc = dev_alloc(h, &h->s_mean[1], (size_t)h->cap * 8))) return rc;
+    if ((rc = dev_alloc(h, &h->s_cov[1], (size_t)h->cap * 64))) return rc;
+  }
+  const int k = (int)(h->submit_count & 1);
+  cudaStream_t cs = h->copy_stream, st = h->stream;
+  if (h->submit_count >= 2) CK(cudaStreamWaitEvent(cs, h->ev_done[k], 0));   // staging set k is free again
+  else CK(cudaStreamWaitEvent(cs, h->ev_done[k], 0));                         // (never-recorded events are complete)
+  CK(cudaMemcpyAsync(h->s_prev[k], prev, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, cs));
+  CK(cudaMemcpyAsync(h->s_curr[k], curr, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, cs));
+  if (prior) CK(cudaMemcpyAsync(h->s_prior[k], prior, (size_t)n * 8 * 4, cudaMemcpyHostToDevice, cs));
+  CK(cudaEventRecord(h->ev_in[k], cs));
+  CK(cudaStreamWaitEvent(st, h->ev_in[k], 0));
+  int rc = forward_any(h, n, h->s_prev[k], h->s_curr[k], prior ? h->s_prior[k] : nullptr, rng, nullptr, h->s_mean[k],
+                       h->s_cov[k], nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(mean, h->s_mean[k], (size_t)n * 8 * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(cov, h->s_cov[k], (size_t)n * 64 * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(h->ev_done[k], st));
+  ++h->submit_count;
+  return UAHN_OK;
+}
+
+int uahn_wait(uahn_handle* h) {
+  if (!h) return UAHN_ERR_INVALID;
+  if (h->copy_stream) CK(cudaStreamSynchronize(h->copy_stream));
+  CK(cudaStreamSynchronize(h->stream));
   return UAHN_OK;
 }
 

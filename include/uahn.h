@@ -107,6 +107,14 @@ UAHN_API int uahn_infer_batch(uahn_handle* h, int n, const uint8_t* prev, const 
 UAHN_API int uahn_infer_batch_device(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior,
                             const uahn_rng* rng, float* mean, float* cov, float* err);
 
+/* Pipelined form of uahn_infer_batch for streams of batches: returns as soon as the work is enqueued.  The H2D copy of
+ * submission i+1 (on an internal copy stream, double-buffered device staging) overlaps the forward of submission i;
+ * results land in `mean` / `cov` (HOST, should be pinned) when uahn_wait() returns.  Philox masks only, no error map.
+ * At most two submissions are in flight: a third call blocks the copy stream until the first has finished. */
+UAHN_API int uahn_submit_batch(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior,
+                      const uahn_rng* rng, float* mean, float* cov);
+UAHN_API int uahn_wait(uahn_handle* h);
+
 UAHN_API int uahn_synchronize(uahn_handle* h);
 UAHN_API void* uahn_stream(uahn_handle* h);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */

@@ -160,6 +160,25 @@ def test_batch_equals_loop_and_is_deterministic(api, wfile):
         assert not np.array_equal(m, m3)     # MC dropout really is stochastic in the seed
 
 
+def test_pipelined_submissions_match_blocking_call(api, wfile):
+    import torch as _t
+    n = 4
+    prev, curr, _, prior = S.synthetic_batch(3 * n, start=800)
+    with api.Uahn(wfile, "prior3", precision="bf16", max_batch=n) as net:
+        ref = [net.infer_batch(prev[i * n:(i + 1) * n], curr[i * n:(i + 1) * n], prior[i * n:(i + 1) * n], seed=2,
+                               first_pair=10 * i) for i in range(3)]
+        pin = lambda a: _t.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        hp, hc, hq = pin(prev), pin(curr), pin(prior.reshape(-1, 8))
+        outs = [(_t.empty(n, 8).pin_memory(), _t.empty(n, 64).pin_memory()) for _ in range(3)]
+        for i in range(3):       # three submissions in flight over two staging sets
+            net.submit_batch_ptrs(n, hp[i * n:].data_ptr(), hc[i * n:].data_ptr(), hq[i * n:].data_ptr(),
+                                  outs[i][0].data_ptr(), outs[i][1].data_ptr(), seed=2, first_pair=10 * i)
+        net.wait()
+        for i in range(3):
+            assert np.array_equal(outs[i][0].numpy(), ref[i][0])
+            assert np.array_equal(outs[i][1].numpy().reshape(n, 8, 8), ref[i][1])
+
+
 def test_philox_masks_replayed_through_oracle(api, wfile, synth_sd):
     n = 2
     prev, curr, _, prior = S.synthetic_batch(n, start=500)
