@@ -106,48 +106,62 @@ __global__ void dlt_kernel(int n, const float* __restrict__ off, const float* __
   }
 }
 
-// d = W8·feat + b8 ; H_b = DLT(pts0, pts0 + d) ; Hout = Hprev ? Hprev·H_b : H_b.   One CTA per pair.
+// d = W8·feat + b8 ; H_b = DLT(pts0, pts0 + d) ; Hout = Hprev ? Hprev·H_b : H_b.
+// FC8_PAIRS pairs per CTA so each 8x5120 weight read from L2 is shared by 4 feature vectors.
 // feat is the last conv output in NHWC order ((h*5+w)*256 + c); W8 was permuted to that order at load.
+constexpr int FC8_PAIRS = 4;
 template <typename T>
-__global__ void __launch_bounds__(256) fc8_dlt_kernel(const T* __restrict__ feat, const float* __restrict__ W8,
+__global__ void __launch_bounds__(256) fc8_dlt_kernel(int n, const T* __restrict__ feat, const float* __restrict__ W8,
                                                        const float* __restrict__ b8, const float* __restrict__ Hprev,
                                                        float* __restrict__ Hout, float* __restrict__ dout) {
-  __shared__ float part[8][8];
-  __shared__ float d_s[8];
-  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const T* f = feat + (size_t)pair * FC_IN;
-  float acc[8];
+  __shared__ float part[8][FC8_PAIRS][8];
+  __shared__ float d_s[FC8_PAIRS][8];
+  const int pair0 = blockIdx.x * FC8_PAIRS, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int np = min(FC8_PAIRS, n - pair0);
+  float acc[FC8_PAIRS][8];
 #pragma unroll
-  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+  for (int p = 0; p < FC8_PAIRS; ++p)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[p][o] = 0.f;
   for (int k = tid; k < FC_IN; k += 256) {
-    const float x = to_f32<T>(f[k]);
+    float w[8], x[FC8_PAIRS];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = fmaf(x, __ldg(W8 + o * FC_IN + k), acc[o]);
+    for (int o = 0; o < 8; ++o) w[o] = __ldg(W8 + o * FC_IN + k);
+#pragma unroll
+    for (int p = 0; p < FC8_PAIRS; ++p) x[p] = p < np ? to_f32<T>(feat[(size_t)(pair0 + p) * FC_IN + k]) : 0.f;
+#pragma unroll
+    for (int p = 0; p < FC8_PAIRS; ++p)
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[p][o] = fmaf(x[p], w[o], acc[p][o]);
   }
 #pragma unroll
-  for (int o = 0; o < 8; ++o) {
+  for (int p = 0; p < FC8_PAIRS; ++p)
 #pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
-    if (lane == 0) part[wid][o] = acc[o];
-  }
+    for (int o = 0; o < 8; ++o) {
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) acc[p][o] += __shfl_xor_sync(0xffffffffu, acc[p][o], s);
+      if (lane == 0) part[wid][p][o] = acc[p][o];
+    }
   __syncthreads();
-  if (tid < 8) {
+  if (tid < FC8_PAIRS * 8) {
+    const int p = tid >> 3, o = tid & 7;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += part[w][tid];
-    s += b8[tid];
-    d_s[tid] = s;
-    if (dout) dout[pair * 8 + tid] = s;
+    for (int w = 0; w < 8; ++w) s += part[w][p][o];
+    s += b8[o];
+    d_s[p][o] = s;
+    if (dout && p < np) dout[(pair0 + p) * 8 + o] = s;
   }
   __syncthreads();
-  if (wid == 0) {
+  if (wid < np) {                       // one warp per pair: DLT + composition
+    const int pair = pair0 + wid;
     float dst[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float x, y;
       corner(i, x, y);
-      dst[2 * i] = __fadd_rn(x, d_s[2 * i]);
-      dst[2 * i + 1] = __fadd_rn(y, d_s[2 * i + 1]);
+      dst[2 * i] = __fadd_rn(x, d_s[wid][2 * i]);
+      dst[2 * i + 1] = __fadd_rn(y, d_s[wid][2 * i + 1]);
     }
     double h[9];
     dlt_warp(dst, h);
@@ -195,11 +209,15 @@ __global__ void __launch_bounds__(256) mc_expand_kernel(const T* __restrict__ fe
       bits = philox_keep8(seed, first_pair + pair, head, 0, s, k8);
     }
     T v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float x = to_f32<T>(f[k8 * 8 + j]);
-      v[j] = from_f32<T>((bits >> j) & 1u ? __fmul_rn(x, KEEP_SCALE) : 0.f);
+    if constexpr (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(f + k8 * 8);     // 8 bf16 features
+    } else {
+      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(f + k8 * 8);
+      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(f + k8 * 8 + 4);
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = from_f32<T>((bits >> j) & 1u ? __fmul_rn(to_f32<T>(v[j]), KEEP_SCALE) : 0.f);
     T* dstp = a + (size_t)s * FC_IN + k8 * 8;
     if constexpr (sizeof(T) == 2) {
       *reinterpret_cast<uint4*>(dstp) = *reinterpret_cast<const uint4*>(v);
@@ -228,7 +246,7 @@ __global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid
                                                         uint64_t first_pair, const uint64_t* __restrict__ rng_dev,
                                                         HeadOut o) {
   if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }
-  __shared__ float w2[2][8][FC_HID];
+  __shared__ __align__(16) float w2[2][8][FC_HID + 4];   // +4 floats: the 8 output rows hit 8 different bank groups
   __shared__ float outv[2][MC][8];
   __shared__ float mu_s[8], var_s[8];
   const int pair = blockIdx.x, tid = threadIdx.x;
@@ -242,20 +260,37 @@ __global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid
     const T* hrow = hid + (((size_t)head * n + pair) * MC + s) * FC_HID;
     const uint8_t* m = keep_masks ? keep_masks + ((size_t)(pair * 2 + head) * MC + s) * MASK_ROW + FC_IN : nullptr;
     float acc = 0.f;
-    for (int j8 = 0; j8 < FC_HID / 8; ++j8) {
-      uint32_t bits;
-      if (m) {
-        bits = 0;
+    // the 8 lanes of one (head, sample) share the hidden-layer keep bits: lane oo draws blocks oo, oo+8, oo+16, oo+24
+    uint32_t mybits[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) bits |= (m[j8 * 8 + j] ? 1u : 0u) << j;
+    for (int jo = 0; jo < 4; ++jo) {
+      const int j8 = jo * 8 + oo;
+      if (m) {
+        mybits[jo] = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mybits[jo] |= (m[j8 * 8 + j] ? 1u : 0u) << j;
       } else {
-        bits = philox_keep8(seed, first_pair + pair, head, 1, s, j8);
+        mybits[jo] = philox_keep8(seed, first_pair + pair, head, 1, s, j8);
       }
+    }
+    const int lane_base = (tid & 31) & ~7;
+#pragma unroll
+    for (int j8 = 0; j8 < FC_HID / 8; ++j8) {
+      const uint32_t bits = __shfl_sync(0xffffffffu, mybits[j8 >> 3], lane_base | (j8 & 7));
+      T hv[8];
+      if constexpr (sizeof(T) == 2) {
+        *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(hrow + j8 * 8);
+      } else {
+        *reinterpret_cast<float4*>(hv) = *reinterpret_cast<const float4*>(hrow + j8 * 8);
+        *reinterpret_cast<float4*>(hv + 4) = *reinterpret_cast<const float4*>(hrow + j8 * 8 + 4);
+      }
+      const float4 wa = *reinterpret_cast<const float4*>(&w2[head][oo][j8 * 8]);
+      const float4 wb = *reinterpret_cast<const float4*>(&w2[head][oo][j8 * 8 + 4]);
+      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float hv = to_f32<T>(hrow[j8 * 8 + j]);
-        const float x = (bits >> j) & 1u ? __fmul_rn(hv, KEEP_SCALE) : 0.f;
-        acc = fmaf(x, w2[head][oo][j8 * 8 + j], acc);
+        const float x = (bits >> j) & 1u ? __fmul_rn(to_f32<T>(hv[j]), KEEP_SCALE) : 0.f;
+        acc = fmaf(x, wv[j], acc);
       }
     }
     acc += head ? b2u[oo] : b2m[oo];
@@ -352,7 +387,7 @@ cudaError_t launch_dlt(int n, const float* off, const float* Hprev, float* Hout,
 template <typename T>
 cudaError_t launch_fc8_dlt(int n, const T* feat, const float* W8, const float* b8, const float* Hprev, float* Hout,
                            float* dout, cudaStream_t st) {
-  fc8_dlt_kernel<T><<<n, 256, 0, st>>>(feat, W8, b8, Hprev, Hout, dout);
+  fc8_dlt_kernel<T><<<(n + FC8_PAIRS - 1) / FC8_PAIRS, 256, 0, st>>>(n, feat, W8, b8, Hprev, Hout, dout);
   return cudaGetLastError();
 }
 template cudaError_t launch_fc8_dlt<float>(int, const float*, const float*, const float*, const float*, float*, float*,
