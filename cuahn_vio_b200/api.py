@@ -131,13 +131,14 @@ class Uahn:
         rc = self._lib.uahn_create(C.byref(cfg), C.byref(self._h))
         if rc:
             msg = self._lib.uahn_last_error(None).decode()
-            self._h = C.c_void_p()
+            self._h = None
             raise UahnError(f"uahn_create failed ({rc}): {msg}")
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            self._lib.uahn_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.uahn_destroy(h)
+            self._h = None        # (no ctypes call here: this also runs at interpreter shutdown)
 
     __del__ = close
 

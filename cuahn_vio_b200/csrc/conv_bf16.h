@@ -21,6 +21,20 @@ struct TmaPlan {
   int n_total = 0;
 };
 
+// Fused block front (conv_fused_front.cu): 7x7 s1 (2 -> C1) + 5x5 s2 (C1 -> C2) in one kernel.
+struct FusedPlan {
+  int enabled = 0;
+  alignas(64) unsigned char tmap[128];
+  int C1 = 0, TX = 0, TY = 0, Wox2 = 0, H1 = 0, W1 = 0;
+  void *b1_image = nullptr, *b2_image = nullptr;
+  float *bias1_x = nullptr, *bias2_x = nullptr;
+};
+int conv_fused_prepare(FusedPlan& plan, const std::vector<float>& wk0, const std::vector<float>& bias0,
+                       const std::vector<float>& wk1, const std::vector<float>& bias1, const ConvGeom& g0,
+                       const ConvGeom& g1, const Tensor& x, std::vector<void*>& allocs, std::string& err);
+cudaError_t launch_conv_fused(const FusedPlan& plan, void* out, const ConvGeom& g1, int n_img, int num_sms,
+                              cudaStream_t st);
+
 struct ConvBf16Weights {
   TmaPlan tma;
   void* b_image = nullptr;   // pre-swizzled B-operand stages in global memory

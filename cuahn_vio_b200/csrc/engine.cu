@@ -81,6 +81,8 @@ struct Block {
   int id = 0, pool = 1;
   bool active = false;
   int chunk_cap = 0;        // pairs held by x and layers[0].out (L2-resident chunking of the block front)
+  FusedPlan fused;          // blocks 3/4 in bf16: conv 0 + conv 1 fused, conv 0's output never reaches HBM
+  Tensor x_unfused;         // small halo-3 input used only by the per-layer stage entry point in fused mode
   Tensor x;                 // 2-channel conv input
   std::vector<Layer> layers;
   float* W8 = nullptr;      // [8][5120] permuted to NHWC feature order (blocks 1-3)
@@ -273,10 +275,14 @@ int build_block(uahn_handle* h, const std::map<std::string, HostTensor>& w, int 
   // pair).  They live in chunk-sized buffers that are re-used for every chunk of `l2_chunk` pairs, so the
   // warp -> conv0 -> conv1 chain of a chunk runs out of L2 and those bytes never round-trip HBM.
   B.chunk_cap = (id >= 3) ? std::min(h->cap, h->l2_chunk) : h->cap;
-  int rc = make_tensor(h, B.x, B.chunk_cap, H, W, 2, (specs[0].k - 1) / 2);
+  const bool try_fuse = h->bf16 && id >= 3 && B.chunk_cap == h->cap && !getenv("UAHN_NO_FUSE");
+  int rc = make_tensor(h, B.x, B.chunk_cap, H, W, 2, try_fuse ? 5 : (specs[0].k - 1) / 2);
   if (rc) return rc;
-  Tensor cur = B.x;
+  const int small_cap = std::min(h->cap, 4);
+  if (try_fuse && (rc = make_tensor(h, B.x_unfused, small_cap, H, W, 2, (specs[0].k - 1) / 2))) return rc;
+  Tensor cur = try_fuse ? B.x_unfused : B.x;
   std::string err;
+  std::vector<float> wk_keep[2], bias_keep[2];
   for (int i = 0; i < nl; ++i) {
     Layer L;
     L.spec = specs[i];
@@ -286,7 +292,7 @@ int build_block(uahn_handle* h, const std::map<std::string, HostTensor>& w, int 
     L.Wo = (W + 2 * p - L.spec.k) / L.spec.stride + 1;
     L.in = cur;
     const int next_pad = i + 1 < nl ? (specs[i + 1].k - 1) / 2 : 0;
-    rc = make_tensor(h, L.out, i == 0 ? B.chunk_cap : h->cap, L.Ho, L.Wo, L.spec.cout, next_pad);
+    rc = make_tensor(h, L.out, i == 0 ? (try_fuse ? small_cap : B.chunk_cap) : h->cap, L.Ho, L.Wo, L.spec.cout, next_pad);
     if (rc) return rc;
     const std::string key = std::string(pre) + L.spec.name + ".0.";
     const HostTensor* wt = find(w, key + "weight", {L.spec.cout, L.spec.cin, L.spec.k, L.spec.k}, err);
@@ -307,9 +313,16 @@ int build_block(uahn_handle* h, const std::map<std::string, HostTensor>& w, int 
       if ((rc = upload(h, &L.w_f32, wk))) return rc;
     }
     if ((rc = upload(h, &L.bias, bt->data))) return rc;
+    if (try_fuse && i < 2) { wk_keep[i] = wk; bias_keep[i] = bt->data; }
     B.layers.push_back(L);
     cur = L.out;
     H = L.Ho; W = L.Wo;
+  }
+  if (try_fuse) {
+    if (conv_fused_prepare(B.fused, wk_keep[0], bias_keep[0], wk_keep[1], bias_keep[1], make_geom(B.layers[0], 1),
+                           make_geom(B.layers[1], 1), B.x, h->allocs, err) < 0)
+      return h->fail(UAHN_ERR_CUDA, "fused front of block %d: %s", id, err.c_str());
+    if (!B.fused.enabled) return h->fail(UAHN_ERR_UNSUPPORTED, "fused front of block %d not available", id);
   }
   if (H != 4 || W != 5 || specs[nl - 1].cout != 256) return h->fail(UAHN_ERR_INVALID, "block %d does not end at 256x4x5", id);
   if (id != 4) {
@@ -373,6 +386,21 @@ int run_block(uahn_handle* h, Block& B, int n, const uint8_t* prev, const uint8_
   int rc;
   const int CH = B.chunk_cap;
   const size_t nl = B.layers.size();
+  if (B.fused.enabled) {
+    if constexpr (sizeof(T) == 2) {
+      static int num_sms = 0;
+      if (!num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+      h->prof_begin(0);
+      LAUNCH(launch_warp_concat_pool<T>(prev, curr, Hcur, B.x, B.pool, n, st));
+      h->prof_end();
+      h->prof_begin(1);
+      LAUNCH(launch_conv_fused(B.fused, B.layers[1].out.p, make_geom(B.layers[1], n), n, num_sms, st));
+      for (size_t i = 2; i < nl; ++i)
+        if ((rc = run_conv<T>(h, B.layers[i], n))) return rc;
+      h->prof_end();
+      return UAHN_OK;
+    }
+  }
   for (int c0 = 0; c0 < n; c0 += CH) {
     const int nc = std::min(CH, n - c0);
     h->prof_begin(0);
@@ -851,6 +879,7 @@ int uahn_stage_conv(uahn_handle* h, const char* layer, int n, const float* in_nc
       if (h->blocks[b].active && !strcmp(layer, l.spec.name)) L = &l;
   if (!L) return h->fail(UAHN_ERR_INVALID, "layer '%s' not in this variant", layer);
   const Tensor& t = L->in;
+  if (n > t.N) return h->fail(UAHN_ERR_INVALID, "layer '%s' accepts at most %d images through this entry point", layer, t.N);
   std::vector<uint8_t> raw((size_t)n * t.pitch_n * h->es, 0);
   for (int i = 0; i < n; ++i)
     for (int c = 0; c < t.C; ++c)

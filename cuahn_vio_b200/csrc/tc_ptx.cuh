@@ -91,6 +91,10 @@ __device__ __forceinline__ int fast_div(int m, unsigned long long magic) {
 }
 
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // One lane of the (converged) warp is elected; the predicate is warp-uniform for the compiler.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
