@@ -27,11 +27,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
+    extra = os.environ.get("UAHN_NVCC_EXTRA", "").split()   # e.g. -DUAHN_FF_PROFILE=1 (per-role cycle counters)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

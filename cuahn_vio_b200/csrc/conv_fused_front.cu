@@ -18,6 +18,7 @@
 //   5. epilogue: D2 -> +bias, LeakyReLU -> bf16 -> staged, coalesced stores into the (haloed NHWC) conv-2 output.
 // conv 1 of tile i+1 overlaps the conv-2 epilogue of tile i (separate TMEM accumulators, mbarrier hand-offs).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -42,7 +43,13 @@ constexpr int SROW = 64 * 2 + 16;                    // conv-2 epilogue staging 
 constexpr int SMEM_BYTES = 1024 + IN_BYTES + B1_STAGES * BSTAGE + B2_STAGES * BSTAGE + 2 * PLANE_BYTES + 128 * SROW +
                            2 * 64 * 4 + 128 * 8 + 32 * 8;
 
+#ifndef UAHN_FF_PROFILE
+#define UAHN_FF_PROFILE 0
+#endif
+__device__ __forceinline__ long long ff_clock() { return UAHN_FF_PROFILE ? clock64() : 0ll; }
+
 struct FusedParams {
+  unsigned long long* dbg;   // optional [grid][24] cycle counters (-DUAHN_FF_PROFILE=1 + UAHN_FF_DEBUG)
   const uint8_t* b1_image;
   const uint8_t* b2_image;
   const float* bias1_x;     // [64]: b1[n % C1]
@@ -109,13 +116,18 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
       for (int s = 0; s < B1_STAGES; ++s) bulk_g2s(smem_u32(sB1 + s * BSTAGE), p.b1_image + (size_t)s * BSTAGE, BSTAGE, BAR(2));
       for (int s = 0; s < B2_STAGES; ++s) bulk_g2s(smem_u32(sB2 + s * BSTAGE), p.b2_image + (size_t)s * BSTAGE, BSTAGE, BAR(2));
       int tcount = 0;
+      long long pw = 0;
+      const long long pbeg = ff_clock();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const int img = fast_div(tile, p.magic_tiles), rem = tile - img * tiles_per_img;
         const int ty = fast_div(rem, p.magic_tx), tx = rem - ty * p.TX;
+        const long long t0 = ff_clock();
         mbar_wait(BAR(1), (tcount & 1) ^ 1);                  // conv-1 MMAs of the previous tile have read the plane
+        pw += ff_clock() - t0;
         mbar_arrive_expect_tx(BAR(0), IN_BYTES);
         tma_load_4d(smem_u32(sIn), &tmap, 0, 7 * tx, 28 * ty, img, BAR(0));
       }
+      if (p.dbg) { p.dbg[blockIdx.x * 24 + 0] = pw; p.dbg[blockIdx.x * 24 + 1] = ff_clock() - pbeg; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -126,15 +138,21 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
     const uint32_t b2_16 = (smem_u32(sB2) & 0x3FFFFu) >> 4, pl16 = (smem_u32(sPl) & 0x3FFFFu) >> 4;
     mbar_wait(BAR(2), 0);
     int tcount = 0;
+    long long mw_in = 0, mw_d1e = 0, mw_pl = 0, mw_d2e = 0, tq;
+    const long long mbeg = ff_clock();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t par = tcount & 1;
       const bool leader = elect_one();
       // ---- conv 1: two 128-row tiles, 7 taps x 2 k-steps each ----
+      tq = ff_clock();
       mbar_wait(BAR(0), par);
+      mw_in += ff_clock() - tq;
       tc_fence_after();
 #pragma unroll
       for (int jt = 0; jt < 2; ++jt) {
+        tq = ff_clock();
         mbar_wait(BAR(5 + jt), par ^ 1);                      // epilogue has drained D1[jt] of the previous tile
+        mw_d1e += ff_clock() - tq;
         tc_fence_after();
         if (leader) {
 #pragma unroll
@@ -152,8 +170,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         __syncwarp();
       }
       // ---- conv 2: 5 taps x (4 + KS2B) k-steps on the planes written by the conv-1 epilogue ----
+      tq = ff_clock();
       mbar_wait(BAR(7), par);
+      mw_pl += ff_clock() - tq;
+      tq = ff_clock();
       mbar_wait(BAR(10), par ^ 1);                            // D2 of the previous tile has been read
+      mw_d2e += ff_clock() - tq;
       tc_fence_after();
       if (leader) {
 #pragma unroll
@@ -174,6 +196,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
       }
       __syncwarp();
     }
+    if (p.dbg && lane == 0) {
+      unsigned long long* d = p.dbg + blockIdx.x * 24;
+      d[2] = mw_in; d[3] = mw_d1e; d[4] = mw_pl; d[5] = mw_d2e; d[6] = ff_clock() - mbeg;
+    }
     tc_fence_before();
   } else {
     // ===================== epilogue warps (2..17) =====================
@@ -187,15 +213,22 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
     long long* qRow = sRowOff + q * 32;
     const uint32_t pl_addr = smem_u32(sPl);
     int tcount = 0;
+    long long ew_ple = 0, ew_d1[2] = {0, 0}, ec_e1 = 0, ew_d2 = 0, ec_e2 = 0, ec_st = 0, tq;
+    const long long ebeg = ff_clock();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t par = tcount & 1;
       const int img = fast_div(tile, p.magic_tiles), rem = tile - img * tiles_per_img;
       const int ty = fast_div(rem, p.magic_tx), tx = rem - ty * p.TX;
       // ---- conv-1 epilogue: D1[jt] -> planes ----
+      tq = ff_clock();
       mbar_wait(BAR(8), par ^ 1);                             // conv-2 MMAs of the previous tile have read the planes
+      ew_ple += ff_clock() - tq;
 #pragma unroll
       for (int jt = 0; jt < 2; ++jt) {
+        tq = ff_clock();
         mbar_wait(BAR(3 + jt), par);
+        ew_d1[jt] += ff_clock() - tq;
+        tq = ff_clock();
         tc_fence_after();
         uint32_t r[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jt * 64 + cg * 16), r);
@@ -223,6 +256,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         const uint32_t row = pl_addr + (uint32_t)((j1 & 1) * PLANE_BYTES + ((j1 >> 1) * 8 + g) * 128);
         st_shared_v4(row + (uint32_t)(((2 * cg) ^ g) << 4), packed[0], packed[1], packed[2], packed[3]);
         st_shared_v4(row + (uint32_t)(((2 * cg + 1) ^ g) << 4), packed[4], packed[5], packed[6], packed[7]);
+        ec_e1 += ff_clock() - tq;
       }
       fence_proxy_async();                                    // generic-proxy writes -> visible to the UMMA reads
       __syncwarp();
@@ -236,7 +270,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
                 (long long)w2 * 128;
         qRow[lane] = off;
       }
+      tq = ff_clock();
       mbar_wait(BAR(9), par);
+      ew_d2 += ff_clock() - tq;
+      tq = ff_clock();
       tc_fence_after();
       {
         uint32_t r[16];
@@ -258,6 +295,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         o[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         o[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
       }
+      ec_e2 += ff_clock() - tq;
+      tq = ff_clock();
       asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "r"(128) : "memory");
       {
         const int rsub = lane >> 3, ch = lane & 7;            // 8 x 16-byte chunks per 128-byte row, 4 rows per store
@@ -270,6 +309,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         }
       }
       asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "r"(128) : "memory");
+      ec_st += ff_clock() - tq;
+    }
+    if (p.dbg && warp == 2 && lane == 0) {
+      unsigned long long* d = p.dbg + blockIdx.x * 24;
+      d[8] = ew_ple; d[9] = ew_d1[0]; d[10] = ew_d1[1]; d[11] = ec_e1; d[12] = ew_d2; d[13] = ec_e2; d[14] = ec_st;
+      d[15] = ff_clock() - ebeg;
     }
   }
   __syncthreads();
@@ -387,6 +432,11 @@ cudaError_t launch_conv_fused(const FusedPlan& plan, void* out, const ConvGeom& 
   p.magic_tx = ((1ull << 40) + p.TX - 1) / p.TX;
   const int tiles = n_img * p.TX * p.TY;
   const int grid = std::min(tiles, num_sms);
+  static unsigned long long* d_dbg = nullptr;
+  const bool debug = UAHN_FF_PROFILE && getenv("UAHN_FF_DEBUG") != nullptr;
+  if (debug && !d_dbg) cudaMalloc(&d_dbg, 24 * 8 * 1024);
+  if (debug) cudaMemsetAsync(d_dbg, 0, 24 * 8 * 1024, st);
+  p.dbg = debug ? d_dbg : nullptr;
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(plan.tmap);
   static bool attr8 = false, attr16 = false;
   if (plan.C1 == 8) {
@@ -403,6 +453,16 @@ cudaError_t launch_conv_fused(const FusedPlan& plan, void* out, const ConvGeom& 
       attr16 = true;
     }
     conv_fused_front_kernel<16, 3><<<grid, FF_THREADS, SMEM_BYTES, st>>>(*tm, p);
+  }
+  if (debug) {
+    std::vector<unsigned long long> h(24 * grid);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+    double a[24] = {0};
+    const double tl = (double)tiles / grid;
+    for (int i = 0; i < grid; ++i) for (int j = 0; j < 24; ++j) a[j] += (double)h[i * 24 + j] / grid / tl;
+    fprintf(stderr, "[uahn-ff] C1=%d tiles/CTA=%.1f per tile (cycles): producer wait_in_empty %.0f of %.0f | mma wait in_full %.0f d1_empty %.0f planes_full %.0f d2_empty %.0f of %.0f | epi(w2) wait planes_empty %.0f d1_full0 %.0f d1_full1 %.0f epi1 %.0f wait d2_full %.0f epi2 %.0f store %.0f of %.0f\n",
+            plan.C1, tl, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]);
   }
   return cudaGetLastError();
 }
