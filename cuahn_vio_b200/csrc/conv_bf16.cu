@@ -209,8 +209,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   } else {
     // ===================== epilogue (warps 6-9): TMEM -> bias/LeakyReLU -> bf16 -> smem -> coalesced global ====
     const int q = warp & 3;                             // TMEM lane quadrant this warp may read
-    uint8_t* myOut = sOut + q * 32 * SROW;
-    long long* myRow = sRowOff + q * 32;
+    const uint32_t out_s = smem_u32(sOut + q * 32 * SROW), row_s = smem_u32(sRowOff + q * 32), bias_s = smem_u32(sBias);
     constexpr int CPR = BN / 8;                         // 16-byte chunks per output row
     constexpr int RPI = CPR >= 32 ? 1 : 32 / CPR;       // rows covered by one warp-wide store
     int tcount = 0;
@@ -226,7 +225,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
           off = p.out_origin_b + (long long)img * p.out_pitch_n_b + (long long)oy * p.out_pitch_y_b +
                 (long long)oxb * p.out_col_step_b + (long long)n0 * 2;
         }
-        myRow[lane] = off;
+        st_shared_b64(row_s + (uint32_t)lane * 8, off);
       }
       mbar_wait(tfull0 + 8 * ab, (tcount >> 1) & 1);
       tc_fence_after();
@@ -239,15 +238,13 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
         uint32_t packed[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float v0 = __uint_as_float(r[2 * e]) + sBias[n0 + c * 16 + 2 * e];
-          float v1 = __uint_as_float(r[2 * e + 1]) + sBias[n0 + c * 16 + 2 * e + 1];
-          if (p.act) { v0 = lrelu(v0); v1 = lrelu(v1); }
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-          packed[e] = *reinterpret_cast<uint32_t*>(&h2);
+          const float2 b2 = ld_shared_f32x2(bias_s + (uint32_t)(n0 + c * 16 + 2 * e) * 4);
+          const float v0 = __uint_as_float(r[2 * e]) + b2.x, v1 = __uint_as_float(r[2 * e + 1]) + b2.y;
+          // LeakyReLU on the packed bf16 pair: the same epilogue arithmetic as the TMA and fused-front kernels
+          packed[e] = p.act ? pack_lrelu_bf16x2(v0, v1) : pack_bf16x2(v0, v1);
         }
-        uint4* o = reinterpret_cast<uint4*>(myOut + lane * SROW + c * 32);
-        o[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        o[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        st_shared_v4(out_s + (uint32_t)(lane * SROW + c * 32), packed[0], packed[1], packed[2], packed[3]);
+        st_shared_v4(out_s + (uint32_t)(lane * SROW + c * 32 + 16), packed[4], packed[5], packed[6], packed[7]);
       }
       tc_fence_before();
       __syncwarp();
@@ -257,9 +254,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
 #pragma unroll 4
         for (int r0 = 0; r0 < 32; r0 += RPI) {
           const int row = r0 + rsub;
-          const long long off = myRow[row];
-          const uint4 v = *reinterpret_cast<const uint4*>(myOut + row * SROW + ch * 16);
-          if (off >= 0) *reinterpret_cast<uint4*>(p.out + off + ch * 16) = v;
+          const long long off = ld_shared_b64(row_s + (uint32_t)row * 8);
+          const uint4 v = ld_shared_v4(out_s + (uint32_t)(row * SROW + ch * 16));
+          if (off >= 0) st_global_v4(p.out + off + ch * 16, v.x, v.y, v.z, v.w);
         }
       }
       __syncwarp();

@@ -62,9 +62,6 @@ struct TmaConvParams {
   unsigned long long* dbg;   // optional [grid][8] cycle counters (UAHN_TMA_DEBUG)
 };
 
-template <int BN>
-constexpr int srow_bytes() { return BN * 2 + 16; }
-
 // Compile-time layer shape: kernel rows KH, conv stride ST, 64-element chunks of the K run and the k-steps (of 16)
 // in chunk 0 / chunk 1.  With these fixed, every tcgen05.mma of a tile has immediate descriptor offsets, so the
 // single issuing lane spends a couple of uniform-datapath adds per MMA instead of table look-ups.
@@ -73,14 +70,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
                                                                        const __grid_constant__ TmaConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * 128;
-  constexpr int SROW = srow_bytes<BN>();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                               // [n_slots][slot_bytes]
   uint8_t* sB = sA + (size_t)p.n_slots * p.slot_bytes;             // [b_stages][BN][128 B], resident
-  uint8_t* sOut = sB + (size_t)p.b_stages * B_STAGE_BYTES;         // [4 warps][32 rows][SROW]
-  float* sBias = reinterpret_cast<float*>(sOut + 128 * SROW);       // [BN]
-  long long* sRowOff = reinterpret_cast<long long*>(sBias + 256);   // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRowOff + 128);
+  float* sBias = reinterpret_cast<float*>(sB + (size_t)p.b_stages * B_STAGE_BYTES);   // [BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
   // bars: [0,S) full, [S,2S) empty, 2S..2S+1 accumulator full, 2S+2..2S+3 accumulator empty, 2S+4 B resident
   const int S = p.n_slots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 5);
@@ -116,6 +110,23 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Both accumulators start out holding the bias (tcgen05.st by the epilogue warps), every MMA accumulates and each
+  // epilogue drain re-arms its columns: no bias add in the epilogue.
+  constexpr int COLS = BN / (EPI_WARPS / 4);            // accumulator columns per epilogue warp (16 for BN = 64)
+  static_assert(COLS == 16, "epilogue is written for 16 accumulator columns per warp");
+  const int q = warp & 3, cg = (warp - 2) >> 2;         // TMEM lane quadrant (hardware rule), column group
+  const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * COLS);
+  uint32_t biasu[COLS];
+  if (warp >= 2) {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) biasu[c] = __float_as_uint(sBias[cg * COLS + c]);
+    tmem_st16(t_lane, biasu);
+    tmem_st16(t_lane + (uint32_t)BN, biasu);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -181,8 +192,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
               // A: the plane shifted by `a` patch rows (a * 8 groups * 128 B) ; B: resident stage (ky, c)
               const uint32_t alo = a16 + (uint32_t)(a * 8 * 128 / 16 + kk * 2);
               const uint32_t blo = b16 + (uint32_t)(((rho + ST * a) * CHUNKS + c) * (BN * 128 / 16) + kk * 2);
-              tc_mma_bf16(d_tmem, DESC_HI | (uint64_t)alo, DESC_HI | (uint64_t)blo, idesc,
-                          (pl == 0 && a == 0 && kk == 0) ? 0u : 1u);
+              tc_mma_bf16(d_tmem, DESC_HI | (uint64_t)alo, DESC_HI | (uint64_t)blo, idesc, 1u);
             }
           }
           tc_commit(empty0 + 8 * slot);
@@ -197,90 +207,48 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
     tc_fence_before();
   } else {
     // ===================== epilogue (warps 2..17) =====================
-    // warp -> TMEM lane quadrant q = warp % 4 (hardware rule) and column group cg: BN/4 columns each.
-    const int q = warp & 3, cg = (warp - 2) >> 2;
-    constexpr int COLS = BN / (EPI_WARPS / 4);          // accumulator columns per warp (16 for BN = 64)
-    constexpr int CPR = BN / 8;                         // 16-byte chunks per output row
-    constexpr int RPI = 32 / CPR;                       // rows per warp-wide store
-    constexpr int ROWS_PER_WARP = 32 / (EPI_WARPS / 4); // rows each warp stores after the quadrant's staging
-    uint8_t* qOut = sOut + q * 32 * SROW;
-    long long* qRow = sRowOff + q * 32;
-    float bias_r[COLS];
-#pragma unroll
-    for (int c = 0; c < COLS; ++c) bias_r[c] = sBias[cg * COLS + c];
+    // TMEM -> registers -> (LeakyReLU on packed bf16x2) -> global: each thread owns 32 contiguous bytes of one
+    // output pixel-group row; no shared-memory staging, no block barriers.
+    const int r = q * 32 + lane, rr = r >> 3, w = r & 7;  // BW = 8
+    const long long thr_off = p.out_origin_b + (long long)rr * p.out_pitch_y_b + (long long)w * p.out_col_step_b +
+                              cg * COLS * 2;
+    const int step_img = (int)gridDim.x / tiles_per_img, step_rem = (int)gridDim.x - step_img * tiles_per_img;
+    int img = (int)blockIdx.x / tiles_per_img, rem = (int)blockIdx.x - img * tiles_per_img;
+    const uint32_t mpx = (uint32_t)((65536 + p.PX - 1) / p.PX);                 // rem < 65536 / PX
     int tcount = 0;
-    long long w_tfull = 0, t_begin = prof_clock(), c_ld = 0, c_math = 0, c_bar1 = 0, c_st = 0, c_bar2 = 0, c_pre = 0;
+    long long w_tfull = 0, t_begin = prof_clock();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const long long tp = prof_clock();
       const int ab = tcount & 1;
-      const int img = fast_div(tile, p.magic_tiles), rem = tile - img * tiles_per_img;
-      const int py = fast_div(rem, p.magic_px), px = rem - py * p.PX;
-      if (cg == 0) {
-        const int r = q * 32 + lane;
-        const int rr = r >> 3, w = r & 7;               // BW = 8
-        const int oy = py * p.BR + rr, oxb = px * p.BW + w;
-        long long off = -1;
-        if (rr < p.BR && oy < p.Ho && oxb < p.Wox)
-          off = p.out_origin_b + (long long)img * p.out_pitch_n_b + (long long)oy * p.out_pitch_y_b +
-                (long long)oxb * p.out_col_step_b;
-        qRow[lane] = off;
-      }
+      const int py = (int)(((uint32_t)rem * mpx) >> 16), px = rem - py * p.PX;
       const long long t0 = prof_clock();
-      c_pre += t0 - tp;
       mbar_wait(tfull0 + 8 * ab, (tcount >> 1) & 1);
-      const long long t1 = prof_clock();
-      w_tfull += t1 - t0;
+      w_tfull += prof_clock() - t0;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + cg * COLS);
-      uint32_t r[COLS];
-#pragma unroll
-      for (int c = 0; c < COLS / 16; ++c) tmem_ld16(taddr + c * 16, r + c * 16);
+      uint32_t acc[COLS];
+      tmem_ld16(t_lane + (uint32_t)(ab * BN), acc);
       tmem_ld_wait();
+      tmem_st16(t_lane + (uint32_t)(ab * BN), biasu);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * ab);     // this warp's slice of the accumulator is in registers
-      const long long t2 = prof_clock();
-      c_ld += t2 - t1;
+      if (lane == 0) mbar_arrive(tempty0 + 8 * ab);       // this warp's slice is in registers and re-armed
+      uint32_t packed[8];
 #pragma unroll
-      for (int c = 0; c < COLS / 16; ++c) {
-        uint32_t packed[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float v0 = __uint_as_float(r[c * 16 + 2 * e]) + bias_r[c * 16 + 2 * e];
-          float v1 = __uint_as_float(r[c * 16 + 2 * e + 1]) + bias_r[c * 16 + 2 * e + 1];
-          if (p.act) { v0 = fmaxf(v0, v0 * LRELU_SLOPE); v1 = fmaxf(v1, v1 * LRELU_SLOPE); }
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-          packed[e] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-        uint4* o = reinterpret_cast<uint4*>(qOut + lane * SROW + (cg * COLS + c * 16) * 2);
-        o[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        o[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      for (int e = 0; e < 8; ++e)
+        packed[e] = p.act ? pack_lrelu_bf16x2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]))
+                          : pack_bf16x2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+      const int oy = py * p.BR + rr, oxb = px * p.BW + w;
+      if (rr < p.BR && oy < p.Ho && oxb < p.Wox) {
+        uint8_t* o = p.out + (thr_off + (long long)img * p.out_pitch_n_b + (long long)(py * p.BR) * p.out_pitch_y_b +
+                              (long long)(px * p.BW) * p.out_col_step_b);
+        st_global_v4(o, packed[0], packed[1], packed[2], packed[3]);
+        st_global_v4(o + 16, packed[4], packed[5], packed[6], packed[7]);
       }
-      // the 4 warps of a quadrant exchange column slices through shared memory: named barrier per quadrant
-      const long long t3 = prof_clock();
-      c_math += t3 - t2;
-      asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "r"(32 * (EPI_WARPS / 4)) : "memory");
-      const long long t4 = prof_clock();
-      c_bar1 += t4 - t3;
-      {
-        const int rsub = lane / CPR, ch = lane % CPR;
-#pragma unroll
-        for (int r0 = 0; r0 < ROWS_PER_WARP; r0 += RPI) {
-          const int row = cg * ROWS_PER_WARP + r0 + rsub;
-          const long long off = qRow[row];
-          const uint4 v = *reinterpret_cast<const uint4*>(qOut + row * SROW + ch * 16);
-          if (off >= 0) *reinterpret_cast<uint4*>(p.out + off + ch * 16) = v;
-        }
-      }
-      const long long t5 = prof_clock();
-      c_st += t5 - t4;
-      asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "r"(32 * (EPI_WARPS / 4)) : "memory");
-      c_bar2 += prof_clock() - t5;
+      rem += step_rem; img += step_img;
+      if (rem >= tiles_per_img) { rem -= tiles_per_img; ++img; }
     }
     if (p.dbg && warp == 2 && lane == 0) {
       p.dbg[blockIdx.x * 8 + 5] = w_tfull; p.dbg[blockIdx.x * 8 + 6] = prof_clock() - t_begin;
-      unsigned long long* e = p.dbg + 8 * 1024 + blockIdx.x * 8;
-      e[0] = c_pre; e[1] = c_ld; e[2] = c_math; e[3] = c_bar1; e[4] = c_st; e[5] = c_bar2;
     }
   }
   __syncthreads();
@@ -293,8 +261,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
 
 template <int BN>
 size_t tma_smem_bytes(int n_slots, int slot_bytes, int b_stages) {
-  return 1024 + (size_t)n_slots * slot_bytes + (size_t)b_stages * BN * 128 + 128 * (size_t)srow_bytes<BN>() + 256 * 4 +
-         128 * 8 + (2 * MAX_SLOTS + 8) * 8 + MAX_OPS * 8 + 16 * 4;
+  return 1024 + (size_t)n_slots * slot_bytes + (size_t)b_stages * BN * 128 + 256 * 4 + (2 * MAX_SLOTS + 8) * 8 + 16 * 4;
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -492,15 +459,11 @@ cudaError_t launch_conv_tma(const TmaPlan& plan, const float* bias, void* out, c
 #undef UAHN_TMA_CASE
   if (lerr != cudaSuccess) return lerr;
   if (debug) {
-    std::vector<unsigned long long> h(8 * grid), h2(8 * grid);
+    std::vector<unsigned long long> h(8 * grid);
     cudaStreamSynchronize(st);
     cudaMemcpy(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
-    cudaMemcpy(h2.data(), d_dbg + 8 * 1024, h2.size() * 8, cudaMemcpyDeviceToHost);
-    double a[8] = {0}, b[8] = {0};
-    for (int i = 0; i < grid; ++i) for (int j = 0; j < 8; ++j) { a[j] += (double)h[i * 8 + j] / grid; b[j] += (double)h2[i * 8 + j] / grid; }
-    const double tl = (double)tiles / grid;
-    fprintf(stderr, "[uahn-tma]   epilogue warp 2 per tile: pre %.0f  wait_tfull %.0f  ld %.0f  math+sts %.0f  bar1 %.0f  store %.0f  bar2 %.0f\n",
-            b[0] / tl, a[5] / tl, b[1] / tl, b[2] / tl, b[3] / tl, b[4] / tl, b[5] / tl);
+    double a[8] = {0};
+    for (int i = 0; i < grid; ++i) for (int j = 0; j < 8; ++j) a[j] += (double)h[i * 8 + j] / grid;
     fprintf(stderr, "[uahn-tma] Cin=%d Cout=%d out=%dx%d tiles/CTA=%.1f planes=%d | producer: wait_empty %.0f of %.0f | mma: wait_tempty %.0f wait_full %.0f of %.0f | epi(w2): wait_tfull %.0f of %.0f  (cycles, mean over CTAs)\n",
             g.Cin, g.Cout, g.Ho, g.Wo, (double)tiles / grid, p.n_planes, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
   }

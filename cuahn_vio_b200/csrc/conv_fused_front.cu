@@ -31,17 +31,17 @@
 namespace uahn {
 namespace {
 
-constexpr int FF_EPI_WARPS = 16;
-constexpr int FF_THREADS = 64 + 32 * FF_EPI_WARPS;
+constexpr int FF_EPI1_WARPS = 8;                     // conv-1 epilogue: 2 per TMEM lane quadrant, 32 columns each
+constexpr int FF_EPI2_WARPS = 8;                     // conv-2 epilogue: 2 per quadrant, 32 columns each
+constexpr int FF_THREADS = 64 + 32 * (FF_EPI1_WARPS + FF_EPI2_WARPS);
 constexpr int IN_ROWS = 38;                          // 32 conv-1 rows + 6 (7x7 halo)
 constexpr int IN_BYTES = IN_ROWS * 8 * 128;          // 38 912
 constexpr int B1_STAGES = 4, B2_STAGES = 10;         // 7 taps packed in pairs; 5 taps x 2 chunks
 constexpr int BSTAGE = 64 * 128;                     // N = 64 rows x 128 B
 constexpr int PLANE_ROWS = 18;                       // t = 0..15 written, +2 rows read only by dummy M rows
 constexpr int PLANE_BYTES = PLANE_ROWS * 8 * 128;    // 18 432
-constexpr int SROW = 64 * 2 + 16;                    // conv-2 epilogue staging row
-constexpr int SMEM_BYTES = 1024 + IN_BYTES + B1_STAGES * BSTAGE + B2_STAGES * BSTAGE + 2 * PLANE_BYTES + 128 * SROW +
-                           2 * 64 * 4 + 128 * 8 + 32 * 8;
+constexpr int SMEM_BYTES = 1024 + 2 * IN_BYTES + B1_STAGES * BSTAGE + B2_STAGES * BSTAGE + 2 * PLANE_BYTES + 2 * 64 * 4 +
+                           32 * 8;
 
 #ifndef UAHN_FF_PROFILE
 #define UAHN_FF_PROFILE 0
@@ -71,16 +71,13 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
   constexpr int G1 = 64 / C1;                        // conv-1 pixels per group
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sIn = smem;                                             // conv-1 input plane
-  uint8_t* sB1 = sIn + IN_BYTES;
+  uint8_t* sIn = smem;                                             // conv-1 input plane, double-buffered
+  uint8_t* sB1 = sIn + 2 * IN_BYTES;
   uint8_t* sB2 = sB1 + B1_STAGES * BSTAGE;
   uint8_t* sPl = sB2 + B2_STAGES * BSTAGE;                         // [2 parities][PLANE_BYTES]
-  uint8_t* sOut = sPl + 2 * PLANE_BYTES;                           // [128][SROW]
-  float* sBias = reinterpret_cast<float*>(sOut + 128 * SROW);      // [2][64]
-  long long* sRowOff = reinterpret_cast<long long*>(sBias + 128);  // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRowOff + 128);
-  // bars: 0 in_full, 1 in_empty, 2 bres, 3-4 d1_full, 5-6 d1_empty, 7 planes_full, 8 planes_empty, 9 d2_full, 10 d2_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* sBias = reinterpret_cast<float*>(sPl + 2 * PLANE_BYTES);  // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
@@ -88,17 +85,23 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
   const int tiles_per_img = p.TX * p.TY;
   const int total_tiles = p.n_img * tiles_per_img;
 
+  // bars: 0-1 in_full[buf], 2 bres, 3-6 d1_full[buf][jt], 7-10 d1_empty[buf][jt], 11 planes_full, 12 d2_full,
+  //       13 d2_empty, 14-15 in_empty[buf]
+  constexpr int B_IN_FULL = 0, B_RES = 2, B_D1_FULL = 3, B_D1_EMPTY = 7, B_PL_FULL = 11, B_D2_FULL = 12,
+                B_D2_EMPTY = 13, B_IN_EMPTY = 14;
+  constexpr uint32_t TMEM_COLS = 512;                    // D1: 2 buffers x 2 row tiles x 64 columns; D2: 64 columns at 256
+  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (warp == 1) {
     if (lane == 0) {
-      mbar_init(BAR(0), 1); mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
-      mbar_init(BAR(3), 1); mbar_init(BAR(4), 1);
-      mbar_init(BAR(5), FF_EPI_WARPS); mbar_init(BAR(6), FF_EPI_WARPS);
-      mbar_init(BAR(7), FF_EPI_WARPS); mbar_init(BAR(8), 1);
-      mbar_init(BAR(9), 1); mbar_init(BAR(10), FF_EPI_WARPS);
+      for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_IN_FULL + i), 1); mbar_init(BAR(B_IN_EMPTY + i), 1); }
+      mbar_init(BAR(B_RES), 1);
+      for (int i = 0; i < 4; ++i) { mbar_init(BAR(B_D1_FULL + i), 1); mbar_init(BAR(B_D1_EMPTY + i), FF_EPI1_WARPS); }
+      mbar_init(BAR(B_PL_FULL), FF_EPI1_WARPS);
+      mbar_init(BAR(B_D2_FULL), 1); mbar_init(BAR(B_D2_EMPTY), FF_EPI2_WARPS);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -107,51 +110,75 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Epilogue warps: TMEM lane quadrant q = warp % 4 (hardware rule).  Warps 2..9 run the conv-1 epilogue, warps
+  // 10..17 the conv-2 epilogue (32 accumulator columns each), so the D1 -> planes hand-off that conv 2 waits for
+  // never queues behind global stores.  The accumulators are pre-loaded with the bias (tcgen05.st): every MMA
+  // accumulates, the epilogues do no bias add, and each drain re-arms its columns.
+  const int q = warp & 3, half = ((warp - 2) >> 2) & 1;
+  const bool epi2_warp = warp >= 2 + FF_EPI1_WARPS;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+  uint32_t biasu[32];                                     // this warp's 32 columns of bias1 (conv-1 side) / bias2
+  if (warp >= 2) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) biasu[c] = __float_as_uint(sBias[(epi2_warp ? 64 : 0) + half * 32 + c]);
+    if (!epi2_warp) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { tmem_st16(t_lane + (uint32_t)(i * 64), biasu); tmem_st16(t_lane + (uint32_t)(i * 64 + 16), biasu + 16); }
+    } else {
+      tmem_st16(t_lane + 256u, biasu); tmem_st16(t_lane + 272u, biasu + 16);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       tma_prefetch_desc(&tmap);
-      mbar_arrive_expect_tx(BAR(2), (uint32_t)((B1_STAGES + B2_STAGES) * BSTAGE));
-      for (int s = 0; s < B1_STAGES; ++s) bulk_g2s(smem_u32(sB1 + s * BSTAGE), p.b1_image + (size_t)s * BSTAGE, BSTAGE, BAR(2));
-      for (int s = 0; s < B2_STAGES; ++s) bulk_g2s(smem_u32(sB2 + s * BSTAGE), p.b2_image + (size_t)s * BSTAGE, BSTAGE, BAR(2));
-      int tcount = 0;
+      mbar_arrive_expect_tx(BAR(B_RES), (uint32_t)((B1_STAGES + B2_STAGES) * BSTAGE));
+      for (int s = 0; s < B1_STAGES; ++s) bulk_g2s(smem_u32(sB1 + s * BSTAGE), p.b1_image + (size_t)s * BSTAGE, BSTAGE, BAR(B_RES));
+      for (int s = 0; s < B2_STAGES; ++s) bulk_g2s(smem_u32(sB2 + s * BSTAGE), p.b2_image + (size_t)s * BSTAGE, BSTAGE, BAR(B_RES));
       long long pw = 0;
       const long long pbeg = ff_clock();
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      for (int k = 0; k < my_tiles; ++k) {
+        const int tile = blockIdx.x + k * gridDim.x;
         const int img = fast_div(tile, p.magic_tiles), rem = tile - img * tiles_per_img;
         const int ty = fast_div(rem, p.magic_tx), tx = rem - ty * p.TX;
         const long long t0 = ff_clock();
-        mbar_wait(BAR(1), (tcount & 1) ^ 1);                  // conv-1 MMAs of the previous tile have read the plane
+        const int ib = k & 1;
+        mbar_wait(BAR(B_IN_EMPTY + ib), ((k >> 1) & 1) ^ 1);  // conv-1 MMAs of tile k-2 have read this buffer
         pw += ff_clock() - t0;
-        mbar_arrive_expect_tx(BAR(0), IN_BYTES);
-        tma_load_4d(smem_u32(sIn), &tmap, 0, 7 * tx, 28 * ty, img, BAR(0));
+        mbar_arrive_expect_tx(BAR(B_IN_FULL + ib), IN_BYTES);
+        tma_load_4d(smem_u32(sIn + ib * IN_BYTES), &tmap, 0, 7 * tx, 28 * ty, img, BAR(B_IN_FULL + ib));
       }
       if (p.dbg) { p.dbg[blockIdx.x * 24 + 0] = pw; p.dbg[blockIdx.x * 24 + 1] = ff_clock() - pbeg; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // Issue order: conv1(0), then per tile k: conv1(k+1), conv2(k).  conv 2 of tile k has to wait for the conv-1
+    // epilogue of tile k (TMEM -> registers -> planes); with conv 1 of the NEXT tile queued in front of it the tensor
+    // pipe works through that wait instead of idling (D1 is double-buffered in TMEM for this).
     constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
     constexpr uint64_t DESC_HI = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t in16 = (smem_u32(sIn) & 0x3FFFFu) >> 4, b1_16 = (smem_u32(sB1) & 0x3FFFFu) >> 4;
     const uint32_t b2_16 = (smem_u32(sB2) & 0x3FFFFu) >> 4, pl16 = (smem_u32(sPl) & 0x3FFFFu) >> 4;
-    mbar_wait(BAR(2), 0);
-    int tcount = 0;
+    mbar_wait(BAR(B_RES), 0);
     long long mw_in = 0, mw_d1e = 0, mw_pl = 0, mw_d2e = 0, tq;
     const long long mbeg = ff_clock();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t par = tcount & 1;
-      const bool leader = elect_one();
-      // ---- conv 1: two 128-row tiles, 7 taps x 2 k-steps each ----
+    const bool leader = elect_one();
+    auto conv1 = [&](int k) {
+      const int buf = k & 1;
       tq = ff_clock();
-      mbar_wait(BAR(0), par);
+      mbar_wait(BAR(B_IN_FULL + buf), (k >> 1) & 1);
       mw_in += ff_clock() - tq;
       tc_fence_after();
 #pragma unroll
       for (int jt = 0; jt < 2; ++jt) {
         tq = ff_clock();
-        mbar_wait(BAR(5 + jt), par ^ 1);                      // epilogue has drained D1[jt] of the previous tile
+        mbar_wait(BAR(B_D1_EMPTY + buf * 2 + jt), ((k >> 1) & 1) ^ 1);   // epilogue has drained this D1 of tile k-2
         mw_d1e += ff_clock() - tq;
         tc_fence_after();
         if (leader) {
@@ -159,22 +186,26 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
           for (int ky = 0; ky < 7; ++ky)
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
-              const uint32_t alo = in16 + (uint32_t)((16 * jt + ky) * (8 * 128 / 16) + kk * 2);
+              const uint32_t alo = in16 + (uint32_t)(buf * (IN_BYTES / 16) + (16 * jt + ky) * (8 * 128 / 16) + kk * 2);
               const uint32_t blo = b1_16 + (uint32_t)((ky >> 1) * (BSTAGE / 16) + (ky & 1) * 4 + kk * 2);
-              tc_mma_bf16(tmem_u + (uint32_t)(jt * 64), DESC_HI | (uint64_t)alo, DESC_HI | (uint64_t)blo, idesc,
-                          (ky | kk) ? 1u : 0u);
+              tc_mma_bf16(tmem_u + (uint32_t)(buf * 128 + jt * 64), DESC_HI | (uint64_t)alo, DESC_HI | (uint64_t)blo, idesc,
+                          1u);                                // D1 was pre-loaded with the bias
             }
-          tc_commit(BAR(3 + jt));
-          if (jt == 1) tc_commit(BAR(1));                     // input plane may be refilled
+          tc_commit(BAR(B_D1_FULL + buf * 2 + jt));
+          if (jt == 1) tc_commit(BAR(B_IN_EMPTY + buf));      // this input buffer may be refilled
         }
         __syncwarp();
       }
+    };
+    if (my_tiles > 0) conv1(0);
+    for (int k = 0; k < my_tiles; ++k) {
+      if (k + 1 < my_tiles) conv1(k + 1);
       // ---- conv 2: 5 taps x (4 + KS2B) k-steps on the planes written by the conv-1 epilogue ----
       tq = ff_clock();
-      mbar_wait(BAR(7), par);
+      mbar_wait(BAR(B_PL_FULL), k & 1);
       mw_pl += ff_clock() - tq;
       tq = ff_clock();
-      mbar_wait(BAR(10), par ^ 1);                            // D2 of the previous tile has been read
+      mbar_wait(BAR(B_D2_EMPTY), (k & 1) ^ 1);                // D2 of the previous tile has been read
       mw_d2e += ff_clock() - tq;
       tc_fence_after();
       if (leader) {
@@ -187,12 +218,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
             for (int kk = 0; kk < (c == 0 ? 4 : KS2B); ++kk) {
               const uint32_t alo = pl16 + (uint32_t)(rho * (PLANE_BYTES / 16) + (a * 8 + c) * (128 / 16) + kk * 2);
               const uint32_t blo = b2_16 + (uint32_t)((ky * 2 + c) * (BSTAGE / 16) + kk * 2);
-              tc_mma_bf16(tmem_u + 128u, DESC_HI | (uint64_t)alo, DESC_HI | (uint64_t)blo, idesc,
-                          (ky | c | kk) ? 1u : 0u);
+              tc_mma_bf16(tmem_u + 256u, DESC_HI | (uint64_t)alo, DESC_HI | (uint64_t)blo, idesc, 1u);
             }
         }
-        tc_commit(BAR(9));
-        tc_commit(BAR(8));                                    // planes may be rewritten
+        tc_commit(BAR(B_D2_FULL));                            // also: the planes may be rewritten
       }
       __syncwarp();
     }
@@ -203,124 +232,130 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
     tc_fence_before();
   } else {
     // ===================== epilogue warps (2..17) =====================
-    const int q = warp & 3, cg = (warp - 2) >> 2;             // TMEM lane quadrant, 16-column group
     const int m = q * 32 + lane;                              // accumulator row
-    const int rr1 = m >> 3, g = m & 7;                        // conv-1: row within the 16-row tile, group
-    float bias1[16], bias2[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) { bias1[c] = sBias[cg * 16 + c]; bias2[c] = sBias[64 + cg * 16 + c]; }
-    uint8_t* qOut = sOut + q * 32 * SROW;
-    long long* qRow = sRowOff + q * 32;
-    const uint32_t pl_addr = smem_u32(sPl);
-    int tcount = 0;
-    long long ew_ple = 0, ew_d1[2] = {0, 0}, ec_e1 = 0, ew_d2 = 0, ec_e2 = 0, ec_st = 0, tq;
-    const long long ebeg = ff_clock();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t par = tcount & 1;
-      const int img = fast_div(tile, p.magic_tiles), rem = tile - img * tiles_per_img;
-      const int ty = fast_div(rem, p.magic_tx), tx = rem - ty * p.TX;
-      // ---- conv-1 epilogue: D1[jt] -> planes ----
-      tq = ff_clock();
-      mbar_wait(BAR(8), par ^ 1);                             // conv-2 MMAs of the previous tile have read the planes
-      ew_ple += ff_clock() - tq;
+    // tile coordinates advance incrementally (no divisions in the loop)
+    const int step_img = (int)gridDim.x / tiles_per_img, step_rem = (int)gridDim.x - step_img * tiles_per_img;
+    int img = (int)blockIdx.x / tiles_per_img, rem = (int)blockIdx.x - img * tiles_per_img;
+    const uint32_t mtx = (uint32_t)((65536 + p.TX - 1) / p.TX);                                     // rem < 65536 / TX
+    long long laps[6] = {0, 0, 0, 0, 0, 0};
+    long long t_prev = ff_clock();
+    const long long ebeg = t_prev;
+    auto lap = [&](int i) {
+      if (UAHN_FF_PROFILE) { const long long now = clock64(); laps[i] += now - t_prev; t_prev = now; }
+    };
+    if (!epi2_warp) {
+      // ---- conv-1 epilogue: D1[buf][jt] -> LeakyReLU -> bf16 planes (conv 2's A operand) ----
+      const int rr1 = m >> 3, g = m & 7;                      // row within the 16-row tile, group
+      // plane rows of this thread's two conv-1 rows (j1 = rr1, 16 + rr1): plane rho = j1 & 1, row (j1 >> 1) * 8 + g;
+      // this warp's 32 columns are 16-byte chunks 4*half .. 4*half+3, address-swizzled with (row & 7) = g
+      const uint32_t pl_addr = smem_u32(sPl);
+      uint32_t prow[2], pch[4];
 #pragma unroll
       for (int jt = 0; jt < 2; ++jt) {
-        tq = ff_clock();
-        mbar_wait(BAR(3 + jt), par);
-        ew_d1[jt] += ff_clock() - tq;
-        tq = ff_clock();
+        const int j1 = 16 * jt + rr1;
+        prow[jt] = pl_addr + (uint32_t)((j1 & 1) * PLANE_BYTES + ((j1 >> 1) * 8 + g) * 128);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) pch[c] = (uint32_t)(((4 * half + c) ^ g) << 4);
+      for (int k = 0; k < my_tiles; ++k) {
+        const int ty = (int)(((uint32_t)rem * mtx) >> 16), tx = rem - ty * p.TX;
+        const int buf = k & 1;
+        const int y0 = 28 * ty - 2, x0 = G1 * 7 * tx - 2;     // first conv-1 row / pixel of the tile region
+        // conv 2's zero padding: conv-1 outputs outside the image must be stored as zeros (border tiles only)
+        const bool border = y0 < 0 || y0 + 31 >= p.H1 || x0 < 0 || x0 + G1 * 8 - 1 >= p.W1;
+        if (k >= 1) mbar_wait(BAR(B_D2_FULL), (k - 1) & 1);   // conv 2 of tile k-1 has read the planes
+        lap(0);
+#pragma unroll
+        for (int jt = 0; jt < 2; ++jt) {
+          mbar_wait(BAR(B_D1_FULL + buf * 2 + jt), (k >> 1) & 1);
+          lap(1);
+          tc_fence_after();
+          uint32_t r[32];
+          tmem_ld32(t_lane + (uint32_t)(buf * 128 + jt * 64), r);
+          tmem_ld_wait();
+          lap(4);
+          uint32_t packed[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) packed[e] = pack_lrelu_bf16x2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+          if (border) {
+            const bool yok = (unsigned)(y0 + 16 * jt + rr1) < (unsigned)p.H1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                     // 16-byte chunk c = columns half*32 + 8c .. +7: one pixel
+              const int x = x0 + G1 * g + (half * 32 + 8 * c) / C1;
+              const bool ok = yok && (unsigned)x < (unsigned)p.W1;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) packed[4 * c + e] = ok ? packed[4 * c + e] : 0u;
+            }
+          }
+          lap(5);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            st_shared_v4(prow[jt] + pch[c], packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+          lap(2);
+        }
+        fence_proxy_async();                                  // generic-proxy writes -> visible to the UMMA reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_PL_FULL));
+        // off the critical path: re-arm both D1 tiles with the bias and hand them back to the MMA warp
+#pragma unroll
+        for (int jt = 0; jt < 2; ++jt) {
+          tmem_st16(t_lane + (uint32_t)(buf * 128 + jt * 64), biasu);
+          tmem_st16(t_lane + (uint32_t)(buf * 128 + jt * 64 + 16), biasu + 16);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(BAR(B_D1_EMPTY + buf * 2)); mbar_arrive(BAR(B_D1_EMPTY + buf * 2 + 1)); }
+        rem += step_rem; img += step_img;
+        if (rem >= tiles_per_img) { rem -= tiles_per_img; ++img; }
+        lap(3);
+      }
+    } else {
+      // ---- conv-2 epilogue: D2 -> LeakyReLU -> bf16 -> global; each thread stores its 64 contiguous bytes ----
+      const int rr2 = m >> 3, w2l = m & 7;
+      const bool row_ok = rr2 < 14 && w2l < 7;
+      const long long thr_off = p.out_origin_b + (long long)rr2 * p.out_pitch_y_b + (long long)w2l * 128 + half * 64;
+      for (int k = 0; k < my_tiles; ++k) {
+        const int ty = (int)(((uint32_t)rem * mtx) >> 16), tx = rem - ty * p.TX;
+        mbar_wait(BAR(B_D2_FULL), k & 1);
+        lap(0);
         tc_fence_after();
-        uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jt * 64 + cg * 16), r);
+        uint32_t r[32];
+        tmem_ld32(t_lane + 256u, r);
         tmem_ld_wait();
+        tmem_st16(t_lane + 256u, biasu);
+        tmem_st16(t_lane + 272u, biasu + 16);
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(5 + jt));
-        const int j1 = 16 * jt + rr1;                         // conv-1 row inside the 32-row region
-        const int y1 = 28 * ty - 2 + j1;
-        const bool yok = (unsigned)y1 < (unsigned)p.H1;
-        const int x1_0 = G1 * (7 * tx + g) - 2;               // first conv-1 pixel of this group
-        uint32_t packed[8];
+        if (lane == 0) mbar_arrive(BAR(B_D2_EMPTY));
+        lap(1);
+        uint32_t packed[16];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          // columns n = cg*16 + 2e, +1  <->  pixel i = n / C1 of the group, channel n % C1
-          const int i = (cg * 16 + 2 * e) / C1;
-          const bool ok = yok && (unsigned)(x1_0 + i) < (unsigned)p.W1;
-          float v0 = __uint_as_float(r[2 * e]) + bias1[2 * e], v1 = __uint_as_float(r[2 * e + 1]) + bias1[2 * e + 1];
-          v0 = fmaxf(v0, v0 * LRELU_SLOPE);
-          v1 = fmaxf(v1, v1 * LRELU_SLOPE);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(ok ? v0 : 0.f, ok ? v1 : 0.f);
-          packed[e] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-        // plane rho = j1 & 1, row R = (j1 >> 1) * 8 + g, 16-byte chunks 2cg, 2cg+1, address-swizzled with R & 7 = g
-        const uint32_t row = pl_addr + (uint32_t)((j1 & 1) * PLANE_BYTES + ((j1 >> 1) * 8 + g) * 128);
-        st_shared_v4(row + (uint32_t)(((2 * cg) ^ g) << 4), packed[0], packed[1], packed[2], packed[3]);
-        st_shared_v4(row + (uint32_t)(((2 * cg + 1) ^ g) << 4), packed[4], packed[5], packed[6], packed[7]);
-        ec_e1 += ff_clock() - tq;
-      }
-      fence_proxy_async();                                    // generic-proxy writes -> visible to the UMMA reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(7));
-      // ---- conv-2 epilogue: D2 -> global ----
-      if (cg == 0) {
-        const int rr = m >> 3, w = m & 7, w2 = 7 * tx + w;
-        long long off = -1;
-        if (rr < 14 && w < 7 && w2 < p.Wox2)
-          off = p.out_origin_b + (long long)img * p.out_pitch_n_b + (long long)(14 * ty + rr) * p.out_pitch_y_b +
-                (long long)w2 * 128;
-        qRow[lane] = off;
-      }
-      tq = ff_clock();
-      mbar_wait(BAR(9), par);
-      ew_d2 += ff_clock() - tq;
-      tq = ff_clock();
-      tc_fence_after();
-      {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 + cg * 16), r);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(10));
-        uint32_t packed[8];
+        for (int e = 0; e < 16; ++e) packed[e] = pack_lrelu_bf16x2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+        if (row_ok && 7 * tx + w2l < p.Wox2) {
+          uint8_t* o = p.out + (thr_off + (long long)img * p.out_pitch_n_b + (long long)(14 * ty) * p.out_pitch_y_b +
+                                (long long)(7 * tx) * 128);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float v0 = __uint_as_float(r[2 * e]) + bias2[2 * e], v1 = __uint_as_float(r[2 * e + 1]) + bias2[2 * e + 1];
-          v0 = fmaxf(v0, v0 * LRELU_SLOPE);
-          v1 = fmaxf(v1, v1 * LRELU_SLOPE);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-          packed[e] = *reinterpret_cast<uint32_t*>(&h2);
+          for (int c = 0; c < 4; ++c)
+            st_global_v4(o + 16 * c, packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
         }
-        uint4* o = reinterpret_cast<uint4*>(qOut + lane * SROW + cg * 32);
-        o[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        o[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        rem += step_rem; img += step_img;
+        if (rem >= tiles_per_img) { rem -= tiles_per_img; ++img; }
+        lap(2);
       }
-      ec_e2 += ff_clock() - tq;
-      tq = ff_clock();
-      asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "r"(128) : "memory");
-      {
-        const int rsub = lane >> 3, ch = lane & 7;            // 8 x 16-byte chunks per 128-byte row, 4 rows per store
-#pragma unroll
-        for (int r0 = 0; r0 < 8; r0 += 4) {
-          const int row = cg * 8 + r0 + rsub;
-          const long long off = qRow[row];
-          const uint4 v = *reinterpret_cast<const uint4*>(qOut + row * SROW + ch * 16);
-          if (off >= 0) *reinterpret_cast<uint4*>(p.out + off + ch * 16) = v;
-        }
-      }
-      asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "r"(128) : "memory");
-      ec_st += ff_clock() - tq;
     }
-    if (p.dbg && warp == 2 && lane == 0) {
-      unsigned long long* d = p.dbg + blockIdx.x * 24;
-      d[8] = ew_ple; d[9] = ew_d1[0]; d[10] = ew_d1[1]; d[11] = ec_e1; d[12] = ew_d2; d[13] = ec_e2; d[14] = ec_st;
-      d[15] = ff_clock() - ebeg;
+    if (p.dbg && lane == 0 && (warp == 2 || warp == 10)) {    // warp 2: conv-1 epilogue, warp 10: conv-2 epilogue
+      unsigned long long* d = p.dbg + blockIdx.x * 24 + (warp == 2 ? 8 : 14);
+      for (int i = 0; i < 4; ++i) d[i] = laps[i];
+      d[4] = ff_clock() - ebeg;
+      if (warp == 2) { d[12] = laps[4]; d[13] = laps[5]; }
     }
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -461,8 +496,11 @@ cudaError_t launch_conv_fused(const FusedPlan& plan, void* out, const ConvGeom& 
     double a[24] = {0};
     const double tl = (double)tiles / grid;
     for (int i = 0; i < grid; ++i) for (int j = 0; j < 24; ++j) a[j] += (double)h[i * 24 + j] / grid / tl;
-    fprintf(stderr, "[uahn-ff] C1=%d tiles/CTA=%.1f per tile (cycles): producer wait_in_empty %.0f of %.0f | mma wait in_full %.0f d1_empty %.0f planes_full %.0f d2_empty %.0f of %.0f | epi(w2) wait planes_empty %.0f d1_full0 %.0f d1_full1 %.0f epi1 %.0f wait d2_full %.0f epi2 %.0f store %.0f of %.0f\n",
-            plan.C1, tl, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]);
+    fprintf(stderr, "[uahn-ff] C1=%d tiles/CTA=%.1f per tile (cycles): producer wait_in_empty %.0f of %.0f | mma wait in_full %.0f d1_empty %.0f planes_full %.0f d2_empty %.0f of %.0f\n",
+            plan.C1, tl, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+    fprintf(stderr, "[uahn-ff]   epi1(w2): wait planes free %.0f | wait d1_full %.0f | ld+pack+sts %.0f | fence+arrive+rearm %.0f | total %.0f   epi2(w10): wait d2_full %.0f | drain %.0f | pack+store %.0f | total %.0f\n",
+            a[8], a[9], a[10], a[11], a[12], a[14], a[15], a[16], a[18]);
+    fprintf(stderr, "[uahn-ff]   epi1 detail: tmem ld %.0f | pack %.0f | sts %.0f\n", a[20], a[21], a[10]);
   }
   return cudaGetLastError();
 }

@@ -306,7 +306,9 @@ def test_fused_front_matches_per_layer_kernels(api, wfile):
         scale = max(1.0, float(np.abs(b).max()))
         assert np.abs(a - b).max() <= 2.0 ** -7 * scale        # one bf16 ulp at the top of the range
         assert np.mean(a != b) < max_frac
-    assert np.abs(outs[True][0] - outs[False][0]).max() < 0.02
+    # both paths sit inside the bf16 budget around the oracle; between themselves they differ by bf16 flips that the
+    # cascade (H3 -> warp -> block 4) amplifies
+    assert np.abs(outs[True][0] - outs[False][0]).max() < BF16_PX
 
 
 @pytest.mark.parametrize("variant", ["prior3", "full"])
