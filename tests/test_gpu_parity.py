@@ -65,7 +65,7 @@ def test_stage_dlt_matches_reference(api, wfile, golden_stages):
 
 def test_stage_warp_indices_bit_exact(api, wfile, golden_stages):
     g = golden_stages
-    with api.Uahn(wfile, "prior1", max_batch=8) as net:
+    with api.Uahn(wfile, "prior1", max_batch=32) as net:
         img = np.repeat(g["warp_src_u8"][None], 4, 0)
         out, ix, iy = net.stage_warp(img, g["warp_H"])
         assert np.array_equal(ix, g["warp_ix"]) and np.array_equal(iy, g["warp_iy"])   # fixtures from the reference
@@ -73,15 +73,16 @@ def test_stage_warp_indices_bit_exact(api, wfile, golden_stages):
         # random homographies incl. large ones that leave the image; oracle computed here
         rng = np.random.default_rng(11)
         Hs = []
-        for t in range(8):
-            disp = (rng.random((4, 2)) * 2 - 1) * (20 if t < 6 else 150)
+        NH = 32      # 2.3 M coordinates: the shared-reciprocal division fast path and (large H) the IEEE fallback
+        for t in range(NH):
+            disp = (rng.random((4, 2)) * 2 - 1) * (20 if t < 24 else 150)
             Hs.append(S.dlt_numpy(S.ORIGIN_4PT.astype(np.float64), S.ORIGIN_4PT + disp).astype(np.float32))
         Hs = np.stack(Hs)
-        img8 = np.repeat(g["warp_src_u8"][None], 8, 0)
+        img8 = np.repeat(g["warp_src_u8"][None], NH, 0)
         out, ix, iy = net.stage_warp(img8, Hs)
         src = O.u8_to_unit(g["warp_src_u8"])
         mism = 0
-        for t in range(8):
+        for t in range(NH):
             Ht = torch.from_numpy(Hs[t])
             rix, riy, _, _ = O.sample_indices(Ht)
             inside = (rix.numpy() >= -1) & (rix.numpy() <= 320) & (riy.numpy() >= -1) & (riy.numpy() <= 224)
