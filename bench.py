@@ -317,6 +317,31 @@ def run_ours(args):
     torch.cuda.synchronize()
     same = bool(torch.equal(hmean.to(dev), mean))
 
+    # ---- e2e over SEQUENCES (uahn_submit_sequence): pair i = (frame i, frame i+1) of one sequence per step, so every
+    # frame crosses PCIe once — the streaming pattern of HomographyNet::load_current_img, batched ------------------
+    seq_frames, _, seq_prior = S.synthetic_sequence(65, seed=20240 + 1000 * rank)
+    reps = (B + 64) // 65 + 1
+    fr = np.concatenate([seq_frames, seq_frames[::-1]] * reps, 0)[:B + 1]       # there-and-back: consecutive frames stay close
+    sq = np.concatenate([seq_prior, -seq_prior[::-1]] * reps, 0)[:B]
+    pfr = torch.from_numpy(np.ascontiguousarray(fr)).pin_memory()
+    psq = torch.from_numpy(np.ascontiguousarray(sq.reshape(B, 8))).pin_memory()
+
+    def step_seq(i):
+        net.submit_sequence_ptrs(B + 1, pfr.data_ptr(), psq.data_ptr(), hmean.data_ptr(), hcov.data_ptr(), seed=1,
+                                 first_pair=rank * B)
+    e2e_seq_value = None
+    if chunk == B:
+        for i in range(2):
+            step_seq(i)
+        net.wait()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            step_seq(i)
+        net.wait()
+        torch.cuda.synchronize()
+        e2e_seq_value = world * B * Ke / (reduce_max_ms(1e3 * (time.perf_counter() - t0), dev) * 1e-3)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -347,6 +372,10 @@ def run_ours(args):
                    "parallelism": f"independent pairs, {world} shard(s), no data-path collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (2 * 71680 + 32),
                 "d2h_bytes_per_step": B * 72 * 4, "steps": Ke, "matches_device_path": same},
+        "e2e_sequence": {"value": e2e_seq_value, "unit": UNIT, "h2d_bytes_per_step": (B + 1) * 71680 + B * 32,
+                         "d2h_bytes_per_step": B * 72 * 4, "steps": Ke,
+                         "what": "uahn_submit_sequence: the step's pairs are consecutive frames of one synthetic sequence "
+                                 "(AR(1) corner walk), each frame uploaded once"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -387,6 +416,32 @@ def run_ours(args):
                                 "p99_ms": 1e3 * ts[int(len(ts) * 0.99)], "calls": len(ts),
                                 "what": "uahn_infer wall clock: prior H2D + forward + 72-float D2H, frames resident"}
         line["latency_batch1"] = lat
+        # ---- BASELINE.json configs[4]: showError variant streamed frame by frame (full cascade + covariance +
+        # photometric-error map), frame k's `curr` reused as frame k+1's `prev` on the device ---------------------
+        n_stream = 2000
+        sf, _, _ = S.synthetic_sequence(64, seed=777)
+        with api.Uahn(wfile, "full", show_error=True, precision=args.precision, device=local, max_batch=1) as ns:
+            ns.load_image(sf[0], 0.0)
+            for i in range(1, 40):
+                ns.load_image(sf[i % 64], float(i))
+                ns.infer(None, seed=1, pair_index=i, want_error=True)
+            ts = []
+            t_all = time.perf_counter()
+            for i in range(n_stream):
+                j = i % 126
+                f = sf[j] if j < 64 else sf[126 - j]                    # there-and-back over the 64 frames
+                t0 = time.perf_counter()
+                ns.load_image(f, float(i))                              # 71 680 B H2D
+                ns.infer(None, seed=1, pair_index=i, want_error=True)    # forward + 72 floats + 71 680 B u8 map D2H
+                ts.append(time.perf_counter() - t0)
+            t_all = time.perf_counter() - t_all
+            ts.sort()
+            line["streaming_show_error"] = {
+                "frames": n_stream, "frames_per_s": n_stream / t_all, "p50_ms": 1e3 * ts[len(ts) // 2],
+                "p90_ms": 1e3 * ts[int(len(ts) * 0.9)], "p99_ms": 1e3 * ts[int(len(ts) * 0.99)],
+                "h2d_bytes_per_frame": 71680, "d2h_bytes_per_frame": 72 * 4 + 71680,
+                "what": "full cascade + covariance + photometric-error map per frame through uahn_load_image + uahn_infer "
+                        "(CUDA-graph replay), synthetic AR(1) sequence"}
 
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = time_reference(args.cpu_seconds, "prior3")

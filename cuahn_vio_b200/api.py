@@ -19,7 +19,8 @@ EXPORTED_SYMBOLS = [
     "uahn_create", "uahn_destroy", "uahn_last_error", "uahn_load_image", "uahn_infer", "uahn_infer_batch",
     "uahn_infer_batch_device", "uahn_synchronize", "uahn_stream", "uahn_launch_count",
     "uahn_latest_inference_time", "uahn_image_count", "uahn_philox_keep_masks", "uahn_stage_dlt",
-    "uahn_stage_warp", "uahn_debug_read", "uahn_profile_enable", "uahn_profile_read", "uahn_stage_conv", "uahn_submit_batch", "uahn_wait",
+    "uahn_stage_warp", "uahn_debug_read", "uahn_profile_enable", "uahn_profile_read", "uahn_stage_conv", "uahn_submit_batch", "uahn_submit_sequence",
+    "uahn_wait",
 ]
 
 
@@ -64,6 +65,8 @@ def load_library(path: str | None = None):
         f.restype = i
     lib.uahn_submit_batch.argtypes = [vp, i, vp, vp, vp, C.POINTER(_Rng), vp, vp]
     lib.uahn_submit_batch.restype = i
+    lib.uahn_submit_sequence.argtypes = [vp, i, vp, vp, C.POINTER(_Rng), vp, vp]
+    lib.uahn_submit_sequence.restype = i
     lib.uahn_wait.argtypes = [vp]
     lib.uahn_wait.restype = i
     lib.uahn_synchronize.argtypes = [vp]
@@ -197,6 +200,12 @@ class Uahn:
         rng = _Rng(seed, first_pair, None)
         self._check(self._lib.uahn_submit_batch(self._h, n, _ptr(prev), _ptr(curr), _ptr(prior), C.byref(rng), _ptr(mean),
                                                 _ptr(cov)))
+
+    def submit_sequence_ptrs(self, n_frames, frames, prior, mean, cov, seed=0, first_pair=0):
+        """Pipelined submission of one sequence: pair i = (frames[i], frames[i+1]); raw pinned-host addresses."""
+        rng = _Rng(seed, first_pair, None)
+        self._check(self._lib.uahn_submit_sequence(self._h, n_frames, _ptr(frames), _ptr(prior), C.byref(rng), _ptr(mean),
+                                                   _ptr(cov)))
 
     def wait(self):
         self._check(self._lib.uahn_wait(self._h))

@@ -139,7 +139,7 @@ struct uahn_handle {
   // pipelined submissions (uahn_submit_batch): copy stream + second staging set
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-  uint8_t *s_prev[2] = {nullptr, nullptr}, *s_curr[2] = {nullptr, nullptr};
+  uint8_t *s_prev[2] = {nullptr, nullptr}, *s_curr[2] = {nullptr, nullptr}, *s_frames[2] = {nullptr, nullptr};
   float *s_prior[2] = {nullptr, nullptr}, *s_mean[2] = {nullptr, nullptr}, *s_cov[2] = {nullptr, nullptr};
   uint64_t submit_count = 0;
   // per-category device timing (uahn_profile_*)
@@ -421,7 +421,8 @@ int run_block(uahn_handle* h, Block& B, int n, const uint8_t* prev, const uint8_
 
 template <typename T>
 int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior, const uahn_rng* rng,
-            const uint8_t* d_masks, float* mean, float* cov, float* err, const uint64_t* rng_dev = nullptr) {
+            const uint8_t* d_masks, float* mean, float* cov, float* err, const uint64_t* rng_dev = nullptr,
+            uint8_t* err_u8 = nullptr) {
   cudaStream_t st = h->stream;
   const int variant = h->cfg.variant;
   const float* Hcur = nullptr;
@@ -463,14 +464,14 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
     }
   }
   h->prof_end();
-  const bool want_err = h->cfg.show_error && err;
+  const bool want_err = h->cfg.show_error && (err || err_u8);
   h->prof_begin(3);
   LAUNCH(launch_mc_final<T>(n, (const T*)h->hid, h->W2m, h->b2m, h->W2u, h->b2u, Hcur, d_masks, seed, first, rng_dev, mean, cov,
                             h->cfg.show_error ? h->Htot : nullptr, h->mc_mean, h->mc_logvar, st));
   h->prof_end();
   if (want_err) {
     h->prof_begin(0);
-    LAUNCH(launch_warp_plain(prev, curr, h->Htot, err, nullptr, nullptr, 1, n, st));
+    LAUNCH(launch_warp_plain(prev, curr, h->Htot, err_u8 ? nullptr : err, err_u8, nullptr, nullptr, 1, n, st));
     h->prof_end();
   }
   h->last_n = n;
@@ -479,10 +480,10 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
 
 int forward_any(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior,
                 const uahn_rng* rng, const uint8_t* d_masks, float* mean, float* cov, float* err,
-                const uint64_t* rng_dev = nullptr) {
+                const uint64_t* rng_dev = nullptr, uint8_t* err_u8 = nullptr) {
   if (n <= 0 || n > h->cap) return h->fail(UAHN_ERR_INVALID, "n=%d outside [1, max_batch=%d]", n, h->cap);
-  return h->bf16 ? forward<__nv_bfloat16>(h, n, prev, curr, prior, rng, d_masks, mean, cov, err, rng_dev)
-                 : forward<float>(h, n, prev, curr, prior, rng, d_masks, mean, cov, err, rng_dev);
+  return h->bf16 ? forward<__nv_bfloat16>(h, n, prev, curr, prior, rng, d_masks, mean, cov, err, rng_dev, err_u8)
+                 : forward<float>(h, n, prev, curr, prior, rng, d_masks, mean, cov, err, rng_dev, err_u8);
 }
 
 }  // namespace
@@ -648,46 +649,79 @@ int uahn_infer_batch(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* 
   return UAHN_OK;
 }
 
-int uahn_submit_batch(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior,
-                      const uahn_rng* rng, float* mean, float* cov) {
-  if (!h) return UAHN_ERR_INVALID;
-  if (!prev || !curr || !mean || !cov) return h->fail(UAHN_ERR_INVALID, "null buffer");
+namespace {
+// copy stream, events and the second staging set of the pipelined entry points
+int ensure_pipeline(uahn_handle* h) {
+  if (h->copy_stream) return UAHN_OK;
+  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+  }
+  h->s_prev[0] = h->d_prev; h->s_curr[0] = h->d_curr; h->s_prior[0] = h->d_prior;
+  h->s_mean[0] = h->d_mean; h->s_cov[0] = h->d_cov;
+  int rc;
+  if ((rc = dev_alloc(h, &h->s_prev[1], (size_t)h->cap * IMG_PIXELS))) return rc;
+  if ((rc = dev_alloc(h, &h->s_curr[1], (size_t)h->cap * IMG_PIXELS))) return rc;
+  if ((rc = dev_alloc(h, &h->s_prior[1], (size_t)h->cap * 8))) return rc;
+  if ((rc = dev_alloc(h, &h->s_mean[1], (size_t)h->cap * 8))) return rc;
+  if ((rc = dev_alloc(h, &h->s_cov[1], (size_t)h->cap * 64))) return rc;
+  return UAHN_OK;
+}
+
+// One pipelined submission.  frames == nullptr: n independent pairs from prev / curr.  frames != nullptr: n + 1
+// consecutive frames, pair i = (frames[i], frames[i+1]) — each frame crosses PCIe once.
+int submit(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const uint8_t* frames, const float* prior,
+           const uahn_rng* rng, float* mean, float* cov) {
   if (n <= 0 || n > h->cap) return h->fail(UAHN_ERR_INVALID, "n=%d outside [1, max_batch=%d]", n, h->cap);
-  if (rng && rng->keep_masks) return h->fail(UAHN_ERR_UNSUPPORTED, "explicit masks are not supported by uahn_submit_batch");
+  if (rng && rng->keep_masks) return h->fail(UAHN_ERR_UNSUPPORTED, "explicit masks are not supported by the pipelined entry points");
   if (h->cfg.variant != UAHN_VARIANT_FULL && !prior) return h->fail(UAHN_ERR_INVALID, "this variant needs a prior");
   CK(cudaSetDevice(h->cfg.device));
-  if (!h->copy_stream) {
-    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
-    }
-    h->s_prev[0] = h->d_prev; h->s_curr[0] = h->d_curr; h->s_prior[0] = h->d_prior;
-    h->s_mean[0] = h->d_mean; h->s_cov[0] = h->d_cov;
-    int rc;
-    if ((rc = dev_alloc(h, &h->s_prev[1], (size_t)h->cap * IMG_PIXELS))) return rc;
-    if ((rc = dev_alloc(h, &h->s_curr[1], (size_t)h->cap * IMG_PIXELS))) return rc;
-    if ((rc = dev_alloc(h, &h->s_prior[1], (size_t)h->cap * 8))) return rc;
-    if ((rc = dev_alloc(h, &h->s_mean[1], (size_t)h->cap * 8))) return rc;
-    if ((rc = dev_alloc(h, &h->s_cov[1], (size_t)h->cap * 64))) return rc;
-  }
+  int rc = ensure_pipeline(h);
+  if (rc) return rc;
+  if (frames && !h->s_frames[0])
+    for (int i = 0; i < 2; ++i)
+      if ((rc = dev_alloc(h, &h->s_frames[i], (size_t)(h->cap + 1) * IMG_PIXELS))) return rc;
   const int k = (int)(h->submit_count & 1);
   cudaStream_t cs = h->copy_stream, st = h->stream;
-  if (h->submit_count >= 2) CK(cudaStreamWaitEvent(cs, h->ev_done[k], 0));   // staging set k is free again
-  else CK(cudaStreamWaitEvent(cs, h->ev_done[k], 0));                         // (never-recorded events are complete)
-  CK(cudaMemcpyAsync(h->s_prev[k], prev, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, cs));
-  CK(cudaMemcpyAsync(h->s_curr[k], curr, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, cs));
+  CK(cudaStreamWaitEvent(cs, h->ev_done[k], 0));   // staging set k is free again (never-recorded events are complete)
+  const uint8_t *dp, *dc;
+  if (frames) {
+    CK(cudaMemcpyAsync(h->s_frames[k], frames, (size_t)(n + 1) * IMG_PIXELS, cudaMemcpyHostToDevice, cs));
+    dp = h->s_frames[k];
+    dc = h->s_frames[k] + IMG_PIXELS;
+  } else {
+    CK(cudaMemcpyAsync(h->s_prev[k], prev, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(h->s_curr[k], curr, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, cs));
+    dp = h->s_prev[k];
+    dc = h->s_curr[k];
+  }
   if (prior) CK(cudaMemcpyAsync(h->s_prior[k], prior, (size_t)n * 8 * 4, cudaMemcpyHostToDevice, cs));
   CK(cudaEventRecord(h->ev_in[k], cs));
   CK(cudaStreamWaitEvent(st, h->ev_in[k], 0));
-  int rc = forward_any(h, n, h->s_prev[k], h->s_curr[k], prior ? h->s_prior[k] : nullptr, rng, nullptr, h->s_mean[k],
-                       h->s_cov[k], nullptr);
+  rc = forward_any(h, n, dp, dc, prior ? h->s_prior[k] : nullptr, rng, nullptr, h->s_mean[k], h->s_cov[k], nullptr);
   if (rc) return rc;
   CK(cudaMemcpyAsync(mean, h->s_mean[k], (size_t)n * 8 * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(cov, h->s_cov[k], (size_t)n * 64 * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(h->ev_done[k], st));
   ++h->submit_count;
   return UAHN_OK;
+}
+}  // namespace
+
+int uahn_submit_batch(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior,
+                      const uahn_rng* rng, float* mean, float* cov) {
+  if (!h) return UAHN_ERR_INVALID;
+  if (!prev || !curr || !mean || !cov) return h->fail(UAHN_ERR_INVALID, "null buffer");
+  return submit(h, n, prev, curr, nullptr, prior, rng, mean, cov);
+}
+
+int uahn_submit_sequence(uahn_handle* h, int n_frames, const uint8_t* frames, const float* prior, const uahn_rng* rng,
+                         float* mean, float* cov) {
+  if (!h) return UAHN_ERR_INVALID;
+  if (!frames || !mean || !cov) return h->fail(UAHN_ERR_INVALID, "null buffer");
+  if (n_frames < 2) return h->fail(UAHN_ERR_STATE, "HNet cannot inference! Only has one image!");   // HomographyNet.cpp:155-158
+  return submit(h, n_frames - 1, nullptr, nullptr, frames, prior, rng, mean, cov);
 }
 
 int uahn_wait(uahn_handle* h) {
@@ -742,12 +776,14 @@ int uahn_infer(uahn_handle* h, const double* prior_px, const uahn_rng* rng, doub
   auto enqueue = [&]() -> int {
     if (need_prior) CK(cudaMemcpyAsync(h->d_prior, h->h_prior, 32, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_rng, h->h_rng, 16, cudaMemcpyHostToDevice, st));
-    int rc = forward_any(h, 1, prev, curr, need_prior ? h->d_prior : nullptr, rng, dm, h->d_mean, h->d_cov,
-                         err_map ? h->d_err : nullptr, h->d_rng);
+    // the error map leaves the device already clamped and truncated to u8 (HomographyNet.cpp:201): 71 680 B of D2H
+    // instead of 286 720 B of floats plus a host conversion loop
+    int rc = forward_any(h, 1, prev, curr, need_prior ? h->d_prior : nullptr, rng, dm, h->d_mean, h->d_cov, nullptr,
+                         h->d_rng, err_map ? reinterpret_cast<uint8_t*>(h->d_err) : nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->h_out, h->d_mean, 8 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h->h_out + 8, h->d_cov, 64 * 4, cudaMemcpyDeviceToHost, st));
-    if (err_map) CK(cudaMemcpyAsync(h->h_out + 72, h->d_err, (size_t)IMG_PIXELS * 4, cudaMemcpyDeviceToHost, st));
+    if (err_map) CK(cudaMemcpyAsync(h->h_out + 72, h->d_err, (size_t)IMG_PIXELS, cudaMemcpyDeviceToHost, st));
     return UAHN_OK;
   };
   const int key = h->ring_curr | (dm ? 2 : 0) | (err_map ? 4 : 0);
@@ -778,12 +814,7 @@ int uahn_infer(uahn_handle* h, const double* prior_px, const uahn_rng* rng, doub
   CK(cudaStreamSynchronize(st));
   for (int i = 0; i < 8; ++i) mean8[i] = h->h_out[i];
   for (int i = 0; i < 64; ++i) cov64[i] = h->h_out[8 + i];
-  if (err_map)
-    for (int i = 0; i < IMG_PIXELS; ++i) {   // .clamp(0,255).to(kU8)  (HomographyNet.cpp:201)
-      float v = h->h_out[72 + i];
-      v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
-      err_map[i] = (uint8_t)v;
-    }
+  if (err_map) memcpy(err_map, h->h_out + 72, IMG_PIXELS);
   return UAHN_OK;
 }
 
@@ -860,7 +891,7 @@ int uahn_stage_warp(uahn_handle* h, int n, const uint8_t* img, const float* Hm, 
   CK(cudaMalloc(&d_iy, (size_t)n * IMG_PIXELS * 2));
   CK(cudaMemcpyAsync(h->d_curr, img, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->Hb[0], Hm, (size_t)n * 36, cudaMemcpyHostToDevice, st));
-  LAUNCH(launch_warp_plain(h->d_curr, h->d_curr, h->Hb[0], d_out, d_ix, d_iy, 0, n, st));
+  LAUNCH(launch_warp_plain(h->d_curr, h->d_curr, h->Hb[0], d_out, nullptr, d_ix, d_iy, 0, n, st));
   CK(cudaMemcpyAsync(out, d_out, (size_t)n * IMG_PIXELS * 4, cudaMemcpyDeviceToHost, st));
   if (ix_nw) CK(cudaMemcpyAsync(ix_nw, d_ix, (size_t)n * IMG_PIXELS * 2, cudaMemcpyDeviceToHost, st));
   if (iy_nw) CK(cudaMemcpyAsync(iy_nw, d_iy, (size_t)n * IMG_PIXELS * 2, cudaMemcpyDeviceToHost, st));

@@ -8,8 +8,9 @@ namespace uahn {
 template <typename T>
 cudaError_t launch_warp_concat_pool(const uint8_t* prev, const uint8_t* curr, const float* Hmat, const Tensor& out,
                                     int pool, int n, cudaStream_t st);
-cudaError_t launch_warp_plain(const uint8_t* prev, const uint8_t* curr, const float* Hmat, float* out, int16_t* ix,
-                              int16_t* iy, int error_map, int n, cudaStream_t st);
+// out (float) or out_u8 (error map clamped to [0,255] and truncated, HomographyNet.cpp:201) — exactly one is non-null
+cudaError_t launch_warp_plain(const uint8_t* prev, const uint8_t* curr, const float* Hmat, float* out, uint8_t* out_u8,
+                              int16_t* ix, int16_t* iy, int error_map, int n, cudaStream_t st);
 
 // conv_f32.cu
 cudaError_t launch_conv_f32(const float* in, const float* wk, const float* bias, float* out, const ConvGeom& g,

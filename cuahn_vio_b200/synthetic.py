@@ -182,6 +182,43 @@ def tiled_batch(n: int, unique: int = 64, base_seed: int = 20240):
     return tile(prev), tile(curr), tile(gt), tile(prior)
 
 
+def synthetic_sequence(n_frames: int, seed: int = 20240, sigma: float = 4.0, rho: float = 0.95,
+                       prior_sigma: float = 2.0):
+    """One synthetic sequence: a textured canvas seen through a homography whose four
+    corner displacements follow a smooth AR(1) random walk (rho, stationary sigma px per coordinate).
+
+    Returns (frames u8[n_frames,224,320], gt f32[n_frames-1,4,2], prior f32[n_frames-1,4,2]); pair i is
+    (frames[i], frames[i+1]), gt[i] the displacement of frame i's corners into frame i+1, prior = gt + N(0, prior_sigma²).
+    """
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed)
+    ch, cw = 288, 384
+    canvas = _texture_canvas(gen, ch, cw)
+    oy, ox = (ch - IMG_H) // 2, (cw - IMG_W) // 2
+    src = ORIGIN_4PT.astype(np.float64)
+    v, u = np.meshgrid(np.arange(IMG_H, dtype=np.float64), np.arange(IMG_W, dtype=np.float64), indexing="ij")
+    pix = np.stack([u.ravel(), v.ravel(), np.ones(u.size)])
+    frames = np.empty((n_frames, IMG_H, IMG_W), np.uint8)
+    Hs = []
+    d = (torch.randn(4, 2, generator=gen) * sigma).numpy().astype(np.float64)
+    for t in range(n_frames):
+        Hm = dlt_numpy(src, src + d)              # canvas-crop pixel -> frame-t pixel
+        Hs.append(Hm)
+        p = np.linalg.inv(Hm) @ pix
+        x, y = p[0] / p[2] + ox, p[1] / p[2] + oy
+        grid = torch.from_numpy(np.stack([x / (cw - 1) * 2 - 1, y / (ch - 1) * 2 - 1], -1).reshape(1, IMG_H, IMG_W, 2)).float()
+        img = torch.nn.functional.grid_sample(canvas, grid, mode="bilinear", padding_mode="border", align_corners=True)
+        frames[t] = (img[0, 0] * 255.0).round().clamp(0, 255).to(torch.uint8).numpy()
+        d = rho * d + np.sqrt(1.0 - rho * rho) * (torch.randn(4, 2, generator=gen) * sigma).numpy()
+    gt = np.empty((n_frames - 1, 4, 2), np.float32)
+    c = np.concatenate([src.T, np.ones((1, 4))])
+    for t in range(n_frames - 1):
+        q = Hs[t + 1] @ np.linalg.inv(Hs[t]) @ c   # frame-t pixel -> frame-(t+1) pixel
+        gt[t] = ((q[:2] / q[2]).T - src).astype(np.float32)
+    prior = gt + (torch.randn(n_frames - 1, 4, 2, generator=gen) * prior_sigma).numpy().astype(np.float32)
+    return frames, gt, prior.astype(np.float32)
+
+
 def torch_dropout_masks(seed: int, mc: int = 16):
     """The four MC-dropout masks the reference consumes after ``torch.manual_seed(seed)``.
 

@@ -113,6 +113,12 @@ UAHN_API int uahn_infer_batch_device(uahn_handle* h, int n, const uint8_t* prev,
  * At most two submissions are in flight: a third call blocks the copy stream until the first has finished. */
 UAHN_API int uahn_submit_batch(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, const float* prior,
                       const uahn_rng* rng, float* mean, float* cov);
+/* The streaming pattern of HomographyNet::load_current_img (HomographyNet.cpp:143: prev <- curr), batched and
+ * pipelined like uahn_submit_batch: `frames` holds n_frames consecutive frames of ONE sequence (n_frames x 224 x 320
+ * u8, HOST), pair i = (frames[i], frames[i+1]); prior / mean / cov have n_frames - 1 rows.  Every frame crosses PCIe
+ * once (71 680 B per pair instead of 143 360 B).  n_frames - 1 <= max_batch. */
+UAHN_API int uahn_submit_sequence(uahn_handle* h, int n_frames, const uint8_t* frames, const float* prior,
+                         const uahn_rng* rng, float* mean, float* cov);
 UAHN_API int uahn_wait(uahn_handle* h);
 
 UAHN_API int uahn_synchronize(uahn_handle* h);

