@@ -22,6 +22,8 @@ EXPORTED_SYMBOLS = [
     "uahn_stage_warp", "uahn_debug_read", "uahn_profile_enable", "uahn_profile_read", "uahn_stage_conv", "uahn_submit_batch", "uahn_submit_sequence",
     "uahn_wait",
 ]
+PREPROC_SYMBOLS = ["uahn_undistort_init_maps", "uahn_set_undistort_maps", "uahn_load_raw_image", "uahn_stage_undistort"]
+EKF_SYMBOLS = ["uahn_ekf_prior_px", "uahn_ekf_update", "uahn_ekf_reset_offsets", "uahn_ekf_iekf_frame"]
 
 
 class UahnError(RuntimeError):
@@ -31,6 +33,24 @@ class UahnError(RuntimeError):
 class _Config(C.Structure):
     _fields_ = [("weights_path", C.c_char_p), ("variant", C.c_int), ("show_error", C.c_int), ("precision", C.c_int),
                 ("device", C.c_int), ("max_batch", C.c_int), ("stream", C.c_void_p)]
+
+
+class EkfState(C.Structure):
+    """uahn_ekf_state (include/uahn_ekf.h): IMU value, the four 4-point offsets, the 27x27 covariance."""
+    _fields_ = [("imu", C.c_double * 16), ("offset", (C.c_double * 3) * 4), ("cov", C.c_double * (27 * 27))]
+
+    @classmethod
+    def from_arrays(cls, imu, offsets, P):
+        s = cls()
+        s.imu[:] = [float(v) for v in np.asarray(imu, np.float64).reshape(16)]
+        for c in range(4):
+            s.offset[c][:] = [float(v) for v in np.asarray(offsets, np.float64).reshape(4, 3)[c]]
+        s.cov[:] = [float(v) for v in np.asarray(P, np.float64).reshape(27 * 27)]
+        return s
+
+    def arrays(self):
+        return (np.array(self.imu[:], np.float64), np.array([list(self.offset[c]) for c in range(4)], np.float64),
+                np.array(self.cov[:], np.float64).reshape(27, 27))
 
 
 class _Rng(C.Structure):
@@ -93,9 +113,53 @@ def load_library(path: str | None = None):
     lib.uahn_stage_conv.restype = i
     lib.uahn_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.uahn_debug_read.restype = C.c_long
+    lib.uahn_undistort_init_maps.argtypes = [i, vp, vp, vp, vp]
+    lib.uahn_undistort_init_maps.restype = i
+    lib.uahn_set_undistort_maps.argtypes = [vp, i, i, vp, vp]
+    lib.uahn_set_undistort_maps.restype = i
+    lib.uahn_load_raw_image.argtypes = [vp, vp, i, i, C.c_size_t, dbl]
+    lib.uahn_load_raw_image.restype = i
+    lib.uahn_stage_undistort.argtypes = [vp, vp, i, i, C.c_size_t, vp]
+    lib.uahn_stage_undistort.restype = i
+    ekf = C.POINTER(EkfState)
+    lib.uahn_ekf_prior_px.argtypes = [ekf, vp, vp]
+    lib.uahn_ekf_prior_px.restype = i
+    lib.uahn_ekf_update.argtypes = [ekf, vp, vp, vp, i, dbl]
+    lib.uahn_ekf_update.restype = i
+    lib.uahn_ekf_reset_offsets.argtypes = [ekf]
+    lib.uahn_ekf_reset_offsets.restype = i
+    lib.uahn_ekf_iekf_frame.argtypes = [vp, vp, ekf, i, dbl, i, i, C.POINTER(_Rng), vp, vp]
+    lib.uahn_ekf_iekf_frame.restype = i
     if path is None:
         _lib = lib
     return lib
+
+
+def undistort_init_maps(fisheye: bool, k, d):
+    """CamBase::initialize_undist_map[_fisheye] through the C ABI (host only): map1, map2 float32 [224, 320]."""
+    lib = load_library()
+    k, d = np.ascontiguousarray(k, np.float64).reshape(4), np.ascontiguousarray(d, np.float64).reshape(4)
+    m1, m2 = np.empty((IMG_H, IMG_W), np.float32), np.empty((IMG_H, IMG_W), np.float32)
+    rc = lib.uahn_undistort_init_maps(int(fisheye), _ptr(k), _ptr(d), _ptr(m1), _ptr(m2))
+    if rc:
+        raise UahnError(f"uahn_undistort_init_maps: error {rc}")
+    return m1, m2
+
+
+def ekf_update(state: "EkfState", mean_px, cov_px, propagated, update_offset: bool, K_net_Cov: float = 10.0):
+    """UpdaterHNet::update through the C ABI (host only)."""
+    lib = load_library()
+    m, c, p = (np.ascontiguousarray(a, np.float64) for a in (mean_px, cov_px, propagated))
+    rc = lib.uahn_ekf_update(C.byref(state), _ptr(m), _ptr(c), _ptr(p), int(update_offset), float(K_net_Cov))
+    if rc:
+        raise UahnError(f"uahn_ekf_update: error {rc}")
+
+
+def ekf_prior_px(state: "EkfState"):
+    lib = load_library()
+    a, b = np.empty(8, np.float64), np.empty(8, np.float64)
+    lib.uahn_ekf_prior_px(C.byref(state), _ptr(a), _ptr(b))
+    return a, b
 
 
 def _ptr(a):
@@ -165,6 +229,20 @@ class Uahn:
         img = np.ascontiguousarray(img, np.uint8)
         self._check(self._lib.uahn_load_image(self._h, _ptr(img), img.shape[0], img.shape[1], img.strides[0], time_stamp))
 
+    def set_undistort_maps(self, raw_rows: int, raw_cols: int, map1: np.ndarray, map2: np.ndarray):
+        m1, m2 = np.ascontiguousarray(map1, np.float32), np.ascontiguousarray(map2, np.float32)
+        self._check(self._lib.uahn_set_undistort_maps(self._h, raw_rows, raw_cols, _ptr(m1), _ptr(m2)))
+
+    def load_raw_image(self, raw: np.ndarray, time_stamp: float = 0.0):
+        raw = np.ascontiguousarray(raw, np.uint8)
+        self._check(self._lib.uahn_load_raw_image(self._h, _ptr(raw), raw.shape[0], raw.shape[1], raw.strides[0], time_stamp))
+
+    def stage_undistort(self, raw: np.ndarray) -> np.ndarray:
+        raw = np.ascontiguousarray(raw, np.uint8)
+        out = np.empty((IMG_H, IMG_W), np.uint8)
+        self._check(self._lib.uahn_stage_undistort(self._h, _ptr(raw), raw.shape[0], raw.shape[1], raw.strides[0], _ptr(out)))
+        return out
+
     def infer(self, prior_px=None, seed: int = 0, pair_index: int = 0, keep_masks: np.ndarray | None = None,
               want_error: bool = False):
         prior = None if prior_px is None else np.ascontiguousarray(prior_px, np.float64).reshape(8)
@@ -206,6 +284,16 @@ class Uahn:
         rng = _Rng(seed, first_pair, None)
         self._check(self._lib.uahn_submit_sequence(self._h, n_frames, _ptr(frames), _ptr(prior), C.byref(rng), _ptr(mean),
                                                    _ptr(cov)))
+
+    def iekf_frame(self, state: "EkfState", max_iter: int = 1, K_net_Cov: float = 10.0, min_images: int = 10,
+                   use_measurement: bool = True, seed: int = 0, pair_index: int = 0, iterative: "Uahn | None" = None):
+        """One camera frame of the IEKF loop (VioManager.cpp:227-275); returns the last network (mean, cov) in px."""
+        mean, cov = np.empty(8, np.float64), np.empty((8, 8), np.float64)
+        rng = _Rng(seed, pair_index, None)
+        self._check(self._lib.uahn_ekf_iekf_frame(self._h, iterative._h if iterative else None, C.byref(state), max_iter,
+                                                  float(K_net_Cov), min_images, int(use_measurement), C.byref(rng),
+                                                  _ptr(mean), _ptr(cov)))
+        return mean, cov
 
     def wait(self):
         self._check(self._lib.uahn_wait(self._h))

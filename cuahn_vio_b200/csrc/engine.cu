@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/uahn.h"
+#include "../../include/uahn_preproc.h"
 #include "common.cuh"
 #include "conv_bf16.h"
 #include "kernels.h"
@@ -119,6 +120,10 @@ struct uahn_handle {
   uint8_t* d_ring = nullptr;
   uint8_t* h_img = nullptr;   // pinned
   float* h_out = nullptr;     // pinned 72 floats (+ err map)
+  // undistort + resize in front of the ring (uahn_preproc.h)
+  float *d_map1 = nullptr, *d_map2 = nullptr;
+  uint8_t *d_raw = nullptr, *h_raw = nullptr;   // h_raw pinned
+  int raw_rows = 0, raw_cols = 0;
   int ring_curr = 0;
   int img_counter = 0;
   double latest_time = -1.0;
@@ -595,6 +600,7 @@ void uahn_destroy(uahn_handle* h) {
   if (h->h_rng) cudaFreeHost(h->h_rng);
   if (h->h_prior) cudaFreeHost(h->h_prior);
   if (h->h_img) cudaFreeHost(h->h_img);
+  if (h->h_raw) cudaFreeHost(h->h_raw);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -815,6 +821,63 @@ int uahn_infer(uahn_handle* h, const double* prior_px, const uahn_rng* rng, doub
   for (int i = 0; i < 8; ++i) mean8[i] = h->h_out[i];
   for (int i = 0; i < 64; ++i) cov64[i] = h->h_out[8 + i];
   if (err_map) memcpy(err_map, h->h_out + 72, IMG_PIXELS);
+  return UAHN_OK;
+}
+
+int uahn_set_undistort_maps(uahn_handle* h, int raw_rows, int raw_cols, const float* map1, const float* map2) {
+  if (!h) return UAHN_ERR_INVALID;
+  if (!map1 || !map2 || raw_rows < 2 || raw_cols < 2 || raw_rows > 32767 || raw_cols > 32767)
+    return h->fail(UAHN_ERR_INVALID, "bad undistort maps / raw size %dx%d", raw_rows, raw_cols);
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  int rc;
+  if (!h->d_map1) {
+    if ((rc = dev_alloc(h, &h->d_map1, (size_t)IMG_PIXELS, false))) return rc;
+    if ((rc = dev_alloc(h, &h->d_map2, (size_t)IMG_PIXELS, false))) return rc;
+  }
+  if ((size_t)raw_rows * raw_cols > (size_t)h->raw_rows * h->raw_cols) {
+    if (h->h_raw) { cudaFreeHost(h->h_raw); h->h_raw = nullptr; }
+    if ((rc = dev_alloc(h, &h->d_raw, (size_t)raw_rows * raw_cols, false))) return rc;
+    CK(cudaMallocHost((void**)&h->h_raw, (size_t)raw_rows * raw_cols));
+  }
+  h->raw_rows = raw_rows; h->raw_cols = raw_cols;
+  CK(cudaMemcpy(h->d_map1, map1, (size_t)IMG_PIXELS * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_map2, map2, (size_t)IMG_PIXELS * 4, cudaMemcpyHostToDevice));
+  return UAHN_OK;
+}
+
+namespace {
+int stage_raw(uahn_handle* h, const uint8_t* raw, int rows, int cols, size_t stride, uint8_t* d_out) {
+  if (!h->d_map1) return h->fail(UAHN_ERR_STATE, "uahn_set_undistort_maps has not been called");
+  if (!raw || rows != h->raw_rows || cols != h->raw_cols || stride < (size_t)cols)
+    return h->fail(UAHN_ERR_INVALID, "raw image must be CV_8UC1 %dx%d (got %dx%d, stride %zu)", h->raw_rows, h->raw_cols, rows,
+                   cols, stride);
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));   // h_raw may still be in flight from the previous frame
+  for (int y = 0; y < rows; ++y) memcpy(h->h_raw + (size_t)y * cols, raw + (size_t)y * stride, cols);
+  CK(cudaMemcpyAsync(h->d_raw, h->h_raw, (size_t)rows * cols, cudaMemcpyHostToDevice, h->stream));
+  LAUNCH(launch_remap_u8(h->d_raw, rows, cols, h->d_map1, h->d_map2, d_out, h->stream));
+  return UAHN_OK;
+}
+}  // namespace
+
+int uahn_load_raw_image(uahn_handle* h, const uint8_t* raw, int rows, int cols, size_t stride, double time_stamp) {
+  if (!h) return UAHN_ERR_INVALID;
+  // prev <- curr is a slot flip (HomographyNet.cpp:143); the remap writes straight into the new curr slot
+  int rc = stage_raw(h, raw, rows, cols, stride, h->d_ring + (size_t)(h->ring_curr ^ 1) * IMG_PIXELS);
+  if (rc) return rc;
+  h->ring_curr ^= 1;
+  h->img_counter++;
+  if (h->img_counter >= 2) h->latest_time = time_stamp;   // HomographyNet.cpp:148
+  return UAHN_OK;
+}
+
+int uahn_stage_undistort(uahn_handle* h, const uint8_t* raw, int rows, int cols, size_t stride, uint8_t* out) {
+  if (!h || !out) return UAHN_ERR_INVALID;
+  int rc = stage_raw(h, raw, rows, cols, stride, h->d_prev);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, h->d_prev, IMG_PIXELS, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return UAHN_OK;
 }
 

@@ -12,6 +12,10 @@ cudaError_t launch_warp_concat_pool(const uint8_t* prev, const uint8_t* curr, co
 cudaError_t launch_warp_plain(const uint8_t* prev, const uint8_t* curr, const float* Hmat, float* out, uint8_t* out_u8,
                               int16_t* ix, int16_t* iy, int error_map, int n, cudaStream_t st);
 
+// cv::remap(INTER_LINEAR, constant-0 border) of a raw u8 frame through float maps into a 224x320 u8 image
+cudaError_t launch_remap_u8(const uint8_t* raw, int rows, int cols, const float* map1, const float* map2, uint8_t* out,
+                            cudaStream_t st);
+
 // conv_f32.cu
 cudaError_t launch_conv_f32(const float* in, const float* wk, const float* bias, float* out, const ConvGeom& g,
                             cudaStream_t st);

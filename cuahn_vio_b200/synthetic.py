@@ -219,6 +219,23 @@ def synthetic_sequence(n_frames: int, seed: int = 20240, sigma: float = 4.0, rho
     return frames, gt, prior.astype(np.float32)
 
 
+def synthetic_raw_frame(seed: int, rows: int = 480, cols: int = 640) -> np.ndarray:
+    """Seeded raw camera frame (u8 [rows, cols]) with structure at several scales; numpy only."""
+    rng = np.random.default_rng(seed)
+    v, u = np.meshgrid(np.arange(rows, dtype=np.float64), np.arange(cols, dtype=np.float64), indexing="ij")
+    acc = np.zeros((rows, cols))
+    for cell, amp in ((8, 1.0), (32, 0.7), (96, 0.5)):
+        n = rng.random((rows // cell + 2, cols // cell + 2))
+        # bilinear upsampling of the coarse noise grid
+        gy, gx = v / cell, u / cell
+        y0, x0 = gy.astype(np.int64), gx.astype(np.int64)
+        fy, fx = gy - y0, gx - x0
+        acc += amp * ((1 - fy) * ((1 - fx) * n[y0, x0] + fx * n[y0, x0 + 1]) + fy * ((1 - fx) * n[y0 + 1, x0] + fx * n[y0 + 1, x0 + 1]))
+    acc += 0.3 * np.sin(u * 0.11) * np.cos(v * 0.07)
+    acc = (acc - acc.min()) / (acc.max() - acc.min())
+    return np.round(acc * 255).astype(np.uint8)
+
+
 def torch_dropout_masks(seed: int, mc: int = 16):
     """The four MC-dropout masks the reference consumes after ``torch.manual_seed(seed)``.
 

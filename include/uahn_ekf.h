@@ -1,0 +1,60 @@
+/*
+ * uahn_ekf.h — host-side consumer of the UAHN outputs: the EKF measurement update and the IEKF loop glue of
+ * CUAHN-VIO ("next" row 1).  Plain C ABI, Eigen-free, double precision, CPU only (27x27 algebra).
+ *
+ * Replaces, for a ROS-free replay harness or a binding that does not want Eigen:
+ *   UpdaterHNet::update                  cuahn_ros/cuahn/src/update/UpdaterHNet.cpp:28-61  (H / Hn: UpdaterHNet.h:56-66)
+ *   State::reset_4pt_offset              cuahn_ros/cuahn/src/state/State.cpp:101-111
+ *   the IEKF loop of VioManager          cuahn_ros/cuahn/src/core/VioManager.cpp:227-275
+ *
+ * State layout = the reference's (State.cpp:31-91): error state [p(3) theta(3) v(3) ba(3) bg(3) f_ul(3) f_bl(3)
+ * f_br(3) f_ur(3)] = 27; IMU value [p(3), q(4, Hamilton, as stored by IMU_CUAHN), v(3), ba(3), bg(3)] = 16;
+ * the four 4-point offsets are 3-vectors in camera-normalised units (pixels / 159.5) of which the network measures
+ * the first two components.
+ */
+#ifndef UAHN_EKF_H_
+#define UAHN_EKF_H_
+
+#include "uahn.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAHN_EKF_DIM 27
+#define UAHN_FOCAL_PX 159.5 /* (320-1)/2 / tan(45 deg): CamBase.h:166-169, VioManager.cpp:234, UpdaterHNet.cpp:31 */
+
+typedef struct uahn_ekf_state {
+  double imu[16];                          /* p, q, v, ba, bg (IMU_CUAHN value order, UpdaterHNet.cpp:45-50)        */
+  double offset[4][3];                     /* UL, BL, BR, UR (State.h: _offset_upperLeft ... _offset_upperRight)    */
+  double cov[UAHN_EKF_DIM * UAHN_EKF_DIM]; /* State::_Cov, row-major                                                 */
+} uahn_ekf_state;
+
+/* prior_px[8] = the (u, v) components of the four offsets x 159.5 (VioManager.cpp:230-234);
+ * propagated[8] (optional) receives the same values in normalised units (what update() takes as 4th argument). */
+UAHN_API int uahn_ekf_prior_px(const uahn_ekf_state* s, double* prior_px8, double* propagated8);
+
+/* UpdaterHNet::update: K = P H^T (H P H^T + K_net_Cov * Cov / 159.5^2)^-1, innovation = mean / 159.5 - propagated,
+ * P <- (I - K H) P, state += K * innovation (quaternion: quatnorm(Ham_quat_update(dtheta) * q)).  update_offset = 0
+ * leaves the four offsets untouched (they are about to be reset).  mean_px / cov_px are the network outputs in pixels /
+ * pixels^2, cov_px row-major 8x8.  Returns UAHN_ERR_INVALID on a singular innovation covariance. */
+UAHN_API int uahn_ekf_update(uahn_ekf_state* s, const double* mean_px8, const double* cov_px64, const double* propagated8,
+                    int update_offset, double K_net_Cov);
+
+/* State::reset_4pt_offset: offsets <- 0, covariance keeps only its IMU 15x15 block. */
+UAHN_API int uahn_ekf_reset_offsets(uahn_ekf_state* s);
+
+/* One camera frame of the IEKF loop (VioManager.cpp:227-275) on the pair currently held by the handle(s):
+ * for it in [0, max_iter): prior <- state offsets x 159.5; uahn_infer on `h` (it == 0) or `h_iter` (it > 0: the
+ * reference's second, "iterative" model, HomographyNet.cpp:209-230; NULL = reuse h); if (image count > min_images)
+ * update with update_offset = (it != max_iter - 1); finally reset the offsets.  Both handles must have been given the
+ * same frames with uahn_load_image.  mean_px8 / cov_px64 (optional) receive the last network output.  The
+ * reference's timestamp gate (HNet->get_latest_inference_time() == time_stamp, :257) is the caller's: pass
+ * use_measurement = 0 to skip the updates.  Needs a GPU (it calls uahn_infer). */
+UAHN_API int uahn_ekf_iekf_frame(uahn_handle* h, uahn_handle* h_iter, uahn_ekf_state* s, int max_iter, double K_net_Cov,
+                        int min_images, int use_measurement, const uahn_rng* rng, double* mean_px8, double* cov_px64);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAHN_EKF_H_ */

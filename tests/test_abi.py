@@ -19,10 +19,14 @@ def lib():
 
 
 def test_header_symbols_exported(lib):
-    hdr = open(os.path.join(ROOT, "include", "uahn.h")).read()
-    declared = set(re.findall(r"\b(uahn_[a-z0-9_]+)\s*\(", hdr))
     from cuahn_vio_b200 import api
-    assert declared == set(api.EXPORTED_SYMBOLS), declared ^ set(api.EXPORTED_SYMBOLS)
+    declared = set()
+    for name, symbols in (("uahn.h", api.EXPORTED_SYMBOLS), ("uahn_ekf.h", api.EKF_SYMBOLS),
+                          ("uahn_preproc.h", api.PREPROC_SYMBOLS)):
+        hdr = open(os.path.join(ROOT, "include", name)).read()
+        found = set(re.findall(r"\b(uahn_[a-z0-9_]+)\s*\(", hdr))
+        assert found == set(symbols), (name, found ^ set(symbols))
+        declared |= found
     for name in declared:
         assert hasattr(lib, name), name
 
