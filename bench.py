@@ -380,10 +380,10 @@ def run_ours(args):
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "traffic_note": "dram__bytes_read+write summed over the 17 conv launches of one step (ncu --set full, "
-                                     "profiles/r01_ncu_conv_layers_b1024.csv); the group is HBM-bound: see hbm_frac_conv_group",
+                     "traffic_note": "dram__bytes_read+write summed over the 15 conv launches of one step (ncu --set full, "
+                                     "profiles/r01_ncu_step_full_b1024.csv)",
                      "hbm_frac_conv_group": (traffic / (conv_ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic and conv_ms_per_step > 0 else None,
-                     "kernel": "conv implicit-GEMM (17 launches per step: blocks 2,3,4)",
+                     "kernel": "conv implicit-GEMM group (15 launches per step: blocks 2,3,4; fused 7x7+5x5 fronts of blocks 3,4)",
                      "algorithmic_flops_per_launch_group": tensor_flops, "ms_per_step": conv_ms_per_step,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})"},
         "stage_ms_per_step": {"warp_concat_pool": prof_ms[0] / K, "conv_stacks": prof_ms[1] / K,
