@@ -47,6 +47,7 @@ struct IgemmParams {
   long long out_origin_b;
   int n_total, n_tiles, m_tiles;
   int act;
+  const uint8_t* mc_bits;   // MC_A mode: keep bits [pair][k8][16 samples] of this head (head_kernels.cu)
 };
 
 template <int BN>
@@ -56,7 +57,11 @@ constexpr int stage_row_bytes() { return BN * 2 + 16; }          // epilogue sta
 
 // Persistent, warp-specialised implicit GEMM.  B_RES: the whole B operand (k_stages x BN x 128 B) stays in
 // shared memory for the lifetime of the CTA (shallow-K layers); otherwise B streams through the stage ring.
-template <int BN, int STAGES, bool B_RES>
+// MC_A: the A operand is the MC-dropout expansion of the block-4 feature, built on the fly (model_to_trace.py:222-224,
+// 272-273): GEMM row (pair, sample) = keep-mask(pair, sample) * feature(pair) / 0.95.  The producer reads each 16-byte
+// feature granule once per pair, scales it, and writes 16 masked copies straight into the swizzled stage; the masked
+// features (327 KB per pair and head) never exist in HBM.
+template <int BN, int STAGES, bool B_RES, bool MC_A = false>
 __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * 128;
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
-        mbar_init(full0 + 8 * s, B_RES ? 128 : 129);   // 128 gather threads (+ the B loader's expect_tx arrive)
+        mbar_init(full0 + 8 * s, B_RES ? 128 : 129);   // 128 producer threads (+ the B loader's expect_tx arrive)
         mbar_init(empty0 + 8 * s, 1);                  // one tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
@@ -103,7 +108,73 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (MC_A && warp < 4) {
+    // ===================== masked-feature producer (MC-dropout GEMM) =====================
+    // thread -> (pair of the tile, granule j of the stage, 8 of the 16 samples); tile = 8 pairs x 16 samples
+    const int pl = tid >> 4, j = tid & 7, hs = (tid >> 3) & 1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.n_tiles) * BM;
+      const int pair = (m0 >> 4) + pl;
+      const bool pvalid = pair * MC < p.M_rows;
+      const uint8_t* f = p.in + (size_t)pair * (FC_IN * 2) + j * 16;
+      const uint8_t* mb = p.mc_bits + ((size_t)pair * (FC_IN / 8) + j) * MC + hs * 8;
+      // feature granule + mask bytes are fetched two stages ahead (L2 latency is several stage times)
+      constexpr int PF = 2;
+      uint4 gq[PF];
+      uint2 mq[PF];
+#pragma unroll
+      for (int d = 0; d < PF; ++d) {
+        gq[d] = make_uint4(0u, 0u, 0u, 0u);
+        mq[d] = make_uint2(0u, 0u);
+        if (pvalid && d < p.k_stages) {
+          gq[d] = __ldg(reinterpret_cast<const uint4*>(f + (size_t)d * 128));
+          mq[d] = __ldg(reinterpret_cast<const uint2*>(mb + (size_t)d * 8 * MC));
+        }
+      }
+      for (int s0 = 0; s0 < p.k_stages; s0 += PF) {
+#pragma unroll
+        for (int d = 0; d < PF; ++d) {
+          const int s = s0 + d;
+          if (s >= p.k_stages) break;
+          const int slot = it % STAGES;
+          const uint4 g = gq[d];
+          const uint2 mk = mq[d];
+          if (pvalid && s + PF < p.k_stages) {
+            gq[d] = __ldg(reinterpret_cast<const uint4*>(f + (size_t)(s + PF) * 128));
+            mq[d] = __ldg(reinterpret_cast<const uint2*>(mb + (size_t)(s + PF) * 8 * MC));
+          }
+          // kept values are scaled by 1/0.95 in fp32 and rounded to bf16 once per pair (same rounding as mc_expand)
+          uint32_t sc[4];
+          {
+            const uint32_t w[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float lo = __uint_as_float(w[c] << 16) * KEEP_SCALE, hi = __uint_as_float(w[c] & 0xFFFF0000u) * KEEP_SCALE;
+              sc[c] = pack_bf16x2(lo, hi);
+            }
+          }
+          mbar_wait(empty0 + 8 * slot, ((it / STAGES) & 1) ^ 1);
+          const uint32_t stage = smem_u32(sA + slot * A_STAGE_BYTES);
+#pragma unroll
+          for (int si = 0; si < 8; ++si) {
+            const uint32_t bits = ((si < 4 ? mk.x : mk.y) >> (8 * (si & 3))) & 0xFFu;
+            uint32_t o[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t b2 = bits >> (2 * c);
+              o[c] = sc[c] & (((b2 & 1u) ? 0x0000FFFFu : 0u) | ((b2 & 2u) ? 0xFFFF0000u : 0u));
+            }
+            const int r = pl * MC + hs * 8 + si;
+            st_shared_v4(stage + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)), o[0], o[1], o[2], o[3]);
+          }
+          fence_proxy_async();                          // generic-proxy writes -> visible to the UMMA reads
+          mbar_arrive(full0 + 8 * slot);
+          ++it;
+        }
+      }
+    }
+  } else if (warp < 4) {
     // ===================== A gather: 128 threads, 8 rows x 1 granule column each per stage ==============
     const int j = tid & 7, rb = tid >> 3;
     const uint32_t dst_off = (uint32_t)rb * 128 + (uint32_t)((j ^ (rb & 7)) << 4);
@@ -274,19 +345,19 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
 template <int BN>
 constexpr size_t fixed_smem() { return 1024 + 128 * (size_t)stage_row_bytes<BN>() + 256 * 4 + 128 * 8 + 64 * 8; }
 
-template <int BN, int STAGES, bool B_RES>
+template <int BN, int STAGES, bool B_RES, bool MC_A = false>
 cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st) {
   const size_t smem = fixed_smem<BN>() + (size_t)STAGES * A_STAGE_BYTES + (size_t)(B_RES ? p.k_stages : STAGES) * BN * 128;
   if (smem > SMEM_LIMIT) return cudaErrorInvalidConfiguration;
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_bf16_kernel<BN, STAGES, B_RES>,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_bf16_kernel<BN, STAGES, B_RES, MC_A>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = smem;
   }
   const int tiles = p.m_tiles * p.n_tiles;
-  conv_igemm_bf16_kernel<BN, STAGES, B_RES><<<std::min(tiles, num_sms), IG_THREADS, smem, st>>>(p);
+  conv_igemm_bf16_kernel<BN, STAGES, B_RES, MC_A><<<std::min(tiles, num_sms), IG_THREADS, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -379,6 +450,36 @@ int conv_bf16_prepare(ConvBf16Weights& wb, const std::vector<float>& wk, const s
   wb.run_granules = rlg;
   wb.ready = 1;
   return 0;
+}
+
+// The two 5120 -> 256 linears of the MC-dropout heads with the dropout expansion fused into the A producer.
+// feat: [n][5120] bf16 (NHWC feature order); mc_bits: this head's keep bits; out: [n*16][256] bf16 hidden activations.
+cudaError_t launch_mc_gemm_bf16(const ConvBf16Weights& wb, const void* feat, const uint8_t* mc_bits, void* out, int n,
+                                cudaStream_t st) {
+  if (!wb.ready || wb.n_total != FC_HID || wb.k_total != FC_IN) return cudaErrorInvalidValue;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  IgemmParams p{};
+  p.in = (const uint8_t*)feat;
+  p.b_image = (const uint8_t*)wb.b_image;
+  p.bias_x = wb.bias_x;
+  p.out = (uint8_t*)out;
+  p.mc_bits = mc_bits;
+  p.Wox = 1; p.rows_per_img = 1;
+  p.M_rows = n * MC;
+  p.magic_rows = (1ull << 40); p.magic_wox = (1ull << 40);
+  p.total_granules = FC_IN / 8; p.run_granules = FC_IN / 8;
+  p.k_steps = FC_IN / 16; p.k_stages = FC_IN / 64;
+  p.out_pitch_n_b = FC_HID * 2; p.out_pitch_y_b = FC_HID * 2; p.out_col_step_b = FC_HID * 2; p.out_origin_b = 0;
+  p.n_total = FC_HID;
+  p.act = 1;
+  p.m_tiles = (p.M_rows + BM - 1) / BM;
+  p.n_tiles = 1;
+  return launch_t<256, 3, false, true>(p, num_sms, st);
 }
 
 cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const float* bias, void* out,

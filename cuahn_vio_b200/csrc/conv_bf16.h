@@ -58,6 +58,8 @@ cudaError_t launch_conv_tma(const TmaPlan& plan, const float* bias, void* out, c
                             cudaStream_t st);
 uint16_t f32_to_bf16_host(float f);
 
+cudaError_t launch_mc_gemm_bf16(const ConvBf16Weights& wb, const void* feat, const uint8_t* mc_bits, void* out, int n,
+                                cudaStream_t st);
 cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const float* bias, void* out,
                              const ConvGeom& g, cudaStream_t st);
 

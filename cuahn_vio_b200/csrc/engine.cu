@@ -107,7 +107,7 @@ struct uahn_handle {
   float *W1m = nullptr, *b1m = nullptr, *W1u = nullptr, *b1u = nullptr;       // [5120][256] fp32 (k' order)
   ConvBf16Weights W1m_b, W1u_b;
   float *W2m = nullptr, *b2m = nullptr, *W2u = nullptr, *b2u = nullptr;
-  void* mcA = nullptr;    // [2][cap][16][5120] T
+  void* mcA = nullptr;    // fp32 mode: [2][cap][16][5120] masked features; bf16 mode: keep bits [2][cap][640][16] bytes
   void* hid = nullptr;    // [2][cap][16][256] T
   float* Hb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // cumulative H after prior(0)/block1..3 ; [4] unused
   float* Htot = nullptr;
@@ -454,21 +454,31 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
   if ((rc = run_block<T>(h, B4, n, prev, curr, Hcur))) return rc;             // model_to_trace.py:261-263
   const T* feat = (const T*)B4.layers.back().out.p;
   const uint64_t seed = rng ? rng->seed : 0, first = rng ? rng->first_pair_index : 0;
-  h->prof_begin(3);
-  LAUNCH(launch_mc_expand<T>(n, feat, (T*)h->mcA, d_masks, seed, first, rng_dev, st));
-  h->prof_end();
-  h->prof_begin(2);
-  for (int head = 0; head < 2; ++head) {
-    ConvGeom g = dense_geom(n * MC, FC_IN, FC_HID, 1);
-    const T* a = (const T*)h->mcA + (size_t)head * n * MC * FC_IN;
-    T* o = (T*)h->hid + (size_t)head * n * MC * FC_HID;
-    if constexpr (sizeof(T) == 4) {
-      LAUNCH(launch_conv_f32((const float*)a, head ? h->W1u : h->W1m, head ? h->b1u : h->b1m, (float*)o, g, st));
-    } else {
-      LAUNCH(launch_conv_bf16(head ? h->W1u_b : h->W1m_b, a, head ? h->b1u : h->b1m, o, g, st));
+  if constexpr (sizeof(T) == 4) {
+    h->prof_begin(3);
+    LAUNCH(launch_mc_expand<T>(n, feat, (T*)h->mcA, d_masks, seed, first, rng_dev, st));
+    h->prof_end();
+    h->prof_begin(2);
+    for (int head = 0; head < 2; ++head) {
+      ConvGeom g = dense_geom(n * MC, FC_IN, FC_HID, 1);
+      const float* a = (const float*)h->mcA + (size_t)head * n * MC * FC_IN;
+      float* o = (float*)h->hid + (size_t)head * n * MC * FC_HID;
+      LAUNCH(launch_conv_f32(a, head ? h->W1u : h->W1m, head ? h->b1u : h->b1m, o, g, st));
     }
+    h->prof_end();
+  } else {
+    // bf16: the dropout expansion is fused into the GEMM's A producer; only the keep BITS (20 KB per pair) are staged
+    h->prof_begin(3);
+    LAUNCH(launch_mc_maskbits(n, (uint8_t*)h->mcA, d_masks, seed, first, rng_dev, st));
+    h->prof_end();
+    h->prof_begin(2);
+    for (int head = 0; head < 2; ++head) {
+      const uint8_t* bits = (const uint8_t*)h->mcA + (size_t)head * n * (FC_IN / 8) * MC;
+      T* o = (T*)h->hid + (size_t)head * n * MC * FC_HID;
+      LAUNCH(launch_mc_gemm_bf16(head ? h->W1u_b : h->W1m_b, feat, bits, o, n, st));
+    }
+    h->prof_end();
   }
-  h->prof_end();
   const bool want_err = h->cfg.show_error && (err || err_u8);
   h->prof_begin(3);
   LAUNCH(launch_mc_final<T>(n, (const T*)h->hid, h->W2m, h->b2m, h->W2u, h->b2u, Hcur, d_masks, seed, first, rng_dev, mean, cov,
@@ -553,7 +563,7 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
   if ((rc = build_head(h, w))) return bail(rc);
   const size_t cap = h->cap;
   uint8_t* p8 = nullptr;
-  if ((rc = dev_alloc(h, &p8, 2 * cap * MC * FC_IN * h->es))) return bail(rc);
+  if ((rc = dev_alloc(h, &p8, h->bf16 ? 2 * cap * (FC_IN / 8) * MC : 2 * cap * MC * FC_IN * h->es))) return bail(rc);
   h->mcA = p8;
   if ((rc = dev_alloc(h, &p8, 2 * cap * MC * FC_HID * h->es))) return bail(rc);
   h->hid = p8;

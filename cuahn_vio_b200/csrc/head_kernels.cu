@@ -228,6 +228,33 @@ __global__ void __launch_bounds__(256) mc_expand_kernel(const T* __restrict__ fe
   }
 }
 
+// Keep-mask BITS of the first MC dropout, consumed by the masked-A producer of the fused 5120->256 GEMMs
+// (conv_bf16.cu): bits[head][pair][k8][sample] bytes, bit j of a byte = keep(k' = 8*k8 + j).  20 KB per pair instead
+// of the 327 KB of materialised, masked features mc_expand_kernel writes.
+__global__ void __launch_bounds__(256) mc_maskbits_kernel(uint8_t* __restrict__ bits_out, int n,
+                                                           const uint8_t* __restrict__ keep_masks, uint64_t seed,
+                                                           uint64_t first_pair, const uint64_t* __restrict__ rng_dev) {
+  if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }
+  const int pair = blockIdx.x, head = blockIdx.y;
+  uint8_t* o = bits_out + ((size_t)head * n + pair) * (FC_IN / 8) * MC;
+  for (int i = threadIdx.x; i < MC * (FC_IN / 8); i += blockDim.x) {
+    const int k8 = i / MC, smp = i - k8 * MC;            // consecutive threads -> consecutive bytes
+    uint32_t bits;
+    if (keep_masks) {
+      const uint8_t* m = keep_masks + ((size_t)(pair * 2 + head) * MC + smp) * MASK_ROW;
+      bits = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kp = k8 * 8 + j, hw = kp >> 8, c = kp & 255;   // kernel order -> reference order c*20 + hw
+        bits |= (m[c * 20 + hw] ? 1u : 0u) << j;
+      }
+    } else {
+      bits = philox_keep8(seed, first_pair + pair, head, 0, smp, k8);
+    }
+    o[i] = (uint8_t)bits;
+  }
+}
+
 struct HeadOut {
   float* mean;     // [n][8]
   float* cov;      // [n][64]
@@ -405,6 +432,12 @@ template cudaError_t launch_mc_expand<float>(int, const float*, float*, const ui
                                              const uint64_t*, cudaStream_t);
 template cudaError_t launch_mc_expand<__nv_bfloat16>(int, const __nv_bfloat16*, __nv_bfloat16*, const uint8_t*,
                                                      uint64_t, uint64_t, const uint64_t*, cudaStream_t);
+
+cudaError_t launch_mc_maskbits(int n, uint8_t* bits, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,
+                               const uint64_t* rng_dev, cudaStream_t st) {
+  mc_maskbits_kernel<<<dim3(n, 2), 256, 0, st>>>(bits, n, keep_masks, seed, first_pair, rng_dev);
+  return cudaGetLastError();
+}
 
 template <typename T>
 cudaError_t launch_mc_final(int n, const T* hid, const float* W2m, const float* b2m, const float* W2u,

@@ -28,6 +28,9 @@ cudaError_t launch_fc8_dlt(int n, const T* feat, const float* W8, const float* b
 template <typename T>
 cudaError_t launch_mc_expand(int n, const T* feat, T* A, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,
                              const uint64_t* rng_dev, cudaStream_t st);
+// bits[head][pair][k8][sample]: keep bits of the first MC dropout for the fused masked GEMM (bf16 path)
+cudaError_t launch_mc_maskbits(int n, uint8_t* bits, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,
+                               const uint64_t* rng_dev, cudaStream_t st);
 template <typename T>
 cudaError_t launch_mc_final(int n, const T* hid, const float* W2m, const float* b2m, const float* W2u,
                             const float* b2u, const float* Hpart1, const uint8_t* keep_masks, uint64_t seed,

@@ -180,6 +180,19 @@ def test_pipelined_submissions_match_blocking_call(api, wfile):
             assert np.array_equal(outs[i][1].numpy().reshape(n, 8, 8), ref[i][1])
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_philox_and_explicit_masks_agree(api, wfile, precision):
+    """In-kernel Philox masks == the same masks replayed as explicit bytes (bf16: fused masked-A GEMM producer;
+    fp32: mc_expand), for a batch that leaves the last 128-row GEMM tile partly empty."""
+    n = 5
+    prev, curr, _, prior = S.synthetic_batch(n, start=900)
+    packed = np.stack([api.philox_keep_masks(77, 11 + i) for i in range(n)])
+    with api.Uahn(wfile, "prior3", precision=precision, max_batch=n) as net:
+        m0, c0, _ = net.infer_batch(prev, curr, prior, seed=77, first_pair=11)
+        m1, c1, _ = net.infer_batch(prev, curr, prior, keep_masks=packed)
+        assert np.array_equal(m0, m1) and np.array_equal(c0, c1)
+
+
 def test_sequence_submission_matches_pairwise_call(api, wfile):
     """uahn_submit_sequence: pair i = (frames[i], frames[i+1]), every frame uploaded once."""
     import torch as _t
