@@ -52,8 +52,13 @@ struct IgemmParams {
 
 template <int BN>
 constexpr int tmem_cols() { return 2 * BN < 32 ? 32 : 2 * BN; }   // two accumulator buffers
+// epilogue staging: the accumulator is drained in chunks of EPI_CHUNK columns, so the staging buffer is 18 KB for every
+// BN and the shared memory it used to take (67 KB at BN = 256) goes to a deeper A/B ring — the cp.async A fill is
+// latency-bound, its throughput is (stages in flight) x 16 KB / L2 latency
 template <int BN>
-constexpr int stage_row_bytes() { return BN * 2 + 16; }          // epilogue staging row (+16 B: conflict-free)
+constexpr int epi_chunk() { return BN < 64 ? BN : 64; }
+template <int BN>
+constexpr int stage_row_bytes() { return epi_chunk<BN>() * 2 + 16; }   // staging row (+16 B: conflict-free)
 
 // Persistent, warp-specialised implicit GEMM.  B_RES: the whole B operand (k_stages x BN x 128 B) stays in
 // shared memory for the lifetime of the CTA (shallow-K layers); otherwise B streams through the stage ring.
@@ -281,8 +286,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
     // ===================== epilogue (warps 6-9): TMEM -> bias/LeakyReLU -> bf16 -> smem -> coalesced global ====
     const int q = warp & 3;                             // TMEM lane quadrant this warp may read
     const uint32_t out_s = smem_u32(sOut + q * 32 * SROW), row_s = smem_u32(sRowOff + q * 32), bias_s = smem_u32(sBias);
-    constexpr int CPR = BN / 8;                         // 16-byte chunks per output row
-    constexpr int RPI = CPR >= 32 ? 1 : 32 / CPR;       // rows covered by one warp-wide store
+    constexpr int CH = epi_chunk<BN>();                 // accumulator columns per staging pass
+    constexpr int CPR = CH / 8;                         // 16-byte chunks per staged row
+    constexpr int RPI = 32 / CPR;                       // rows covered by one warp-wide store
     int tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int ab = tcount & 1;
@@ -301,36 +307,41 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
       mbar_wait(tfull0 + 8 * ab, (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
 #pragma unroll
-      for (int c = 0; c < BN / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c * 16, r);
-        tmem_ld_wait();
-        uint32_t packed[8];
+        for (int c = 0; c < CH / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0 + c * 16, r);
+          tmem_ld_wait();
+          uint32_t packed[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float2 b2 = ld_shared_f32x2(bias_s + (uint32_t)(n0 + c * 16 + 2 * e) * 4);
-          const float v0 = __uint_as_float(r[2 * e]) + b2.x, v1 = __uint_as_float(r[2 * e + 1]) + b2.y;
-          // LeakyReLU on the packed bf16 pair: the same epilogue arithmetic as the TMA and fused-front kernels
-          packed[e] = p.act ? pack_lrelu_bf16x2(v0, v1) : pack_bf16x2(v0, v1);
+          for (int e = 0; e < 8; ++e) {
+            const float2 b2 = ld_shared_f32x2(bias_s + (uint32_t)(n0 + c0 + c * 16 + 2 * e) * 4);
+            const float v0 = __uint_as_float(r[2 * e]) + b2.x, v1 = __uint_as_float(r[2 * e + 1]) + b2.y;
+            // LeakyReLU on the packed bf16 pair: the same epilogue arithmetic as the TMA and fused-front kernels
+            packed[e] = p.act ? pack_lrelu_bf16x2(v0, v1) : pack_bf16x2(v0, v1);
+          }
+          st_shared_v4(out_s + (uint32_t)(lane * SROW + c * 32), packed[0], packed[1], packed[2], packed[3]);
+          st_shared_v4(out_s + (uint32_t)(lane * SROW + c * 32 + 16), packed[4], packed[5], packed[6], packed[7]);
         }
-        st_shared_v4(out_s + (uint32_t)(lane * SROW + c * 32), packed[0], packed[1], packed[2], packed[3]);
-        st_shared_v4(out_s + (uint32_t)(lane * SROW + c * 32 + 16), packed[4], packed[5], packed[6], packed[7]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * ab);     // accumulator free: the next tile's MMAs may start
-      if (CPR <= 32) {
-        const int rsub = lane / (CPR < 32 ? CPR : 32), ch = lane % (CPR < 32 ? CPR : 32);
+        if (c0 + CH >= BN) {                              // the whole accumulator is in registers / staged
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * ab);   // the next tile's MMAs may start
+        } else {
+          __syncwarp();
+        }
+        const int rsub = lane / CPR, ch = lane % CPR;
 #pragma unroll 4
         for (int r0 = 0; r0 < 32; r0 += RPI) {
           const int row = r0 + rsub;
           const long long off = ld_shared_b64(row_s + (uint32_t)row * 8);
           const uint4 v = ld_shared_v4(out_s + (uint32_t)(row * SROW + ch * 16));
-          if (off >= 0) st_global_v4(p.out + off + ch * 16, v.x, v.y, v.z, v.w);
+          if (off >= 0) st_global_v4(p.out + off + c0 * 2 + ch * 16, v.x, v.y, v.z, v.w);
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   __syncthreads();
@@ -479,7 +490,7 @@ cudaError_t launch_mc_gemm_bf16(const ConvBf16Weights& wb, const void* feat, con
   p.act = 1;
   p.m_tiles = (p.M_rows + BM - 1) / BM;
   p.n_tiles = 1;
-  return launch_t<256, 3, false, true>(p, num_sms, st);
+  return launch_t<256, 4, false, true>(p, num_sms, st);
 }
 
 cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const float* bias, void* out,
@@ -529,11 +540,11 @@ cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const fl
   // B resident in shared memory when the whole operand of this N tile fits next to a 4-stage A ring
   const bool res = p.n_tiles == 1 && (size_t)p.k_stages * bn * 128 <= 112 * 1024;
   switch (bn) {
-    case 256: return launch_t<256, 3, false>(p, num_sms, st);
-    case 128: return res ? launch_t<128, 4, true>(p, num_sms, st) : launch_t<128, 4, false>(p, num_sms, st);
-    case 64: return res ? launch_t<64, 4, true>(p, num_sms, st) : launch_t<64, 6, false>(p, num_sms, st);
-    case 32: return res ? launch_t<32, 4, true>(p, num_sms, st) : launch_t<32, 6, false>(p, num_sms, st);
-    case 16: return res ? launch_t<16, 4, true>(p, num_sms, st) : launch_t<16, 6, false>(p, num_sms, st);
+    case 256: return launch_t<256, 4, false>(p, num_sms, st);
+    case 128: return res ? launch_t<128, 5, true>(p, num_sms, st) : launch_t<128, 6, false>(p, num_sms, st);
+    case 64: return res ? launch_t<64, 5, true>(p, num_sms, st) : launch_t<64, 8, false>(p, num_sms, st);
+    case 32: return res ? launch_t<32, 5, true>(p, num_sms, st) : launch_t<32, 8, false>(p, num_sms, st);
+    case 16: return res ? launch_t<16, 5, true>(p, num_sms, st) : launch_t<16, 8, false>(p, num_sms, st);
     default: return cudaErrorInvalidValue;
   }
 }

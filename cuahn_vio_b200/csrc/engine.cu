@@ -66,6 +66,7 @@ const LayerSpec B1[] = {{"block_1_1", 128, 2, 7, 2}, {"block_1_2", 128, 128, 5, 
 const LayerSpec B2[] = {{"block_2_1", 64, 2, 7, 2}, {"block_2_2", 128, 64, 5, 2}, {"block_2_3", 256, 128, 3, 2}, {"block_2_4", 256, 256, 3, 2}};
 const LayerSpec B3[] = {{"block_3_0", 16, 2, 7, 1}, {"block_3_1", 32, 16, 5, 2}, {"block_3_2", 64, 32, 3, 2}, {"block_3_3", 128, 64, 3, 2}, {"block_3_4", 256, 128, 3, 2}, {"block_3_5", 256, 256, 3, 2}};
 const LayerSpec B4[] = {{"block_4_0", 8, 2, 7, 1}, {"block_4_1", 16, 8, 5, 2}, {"block_4_2", 32, 16, 3, 2}, {"block_4_3", 64, 32, 3, 2}, {"block_4_4", 128, 64, 3, 2}, {"block_4_5", 256, 128, 3, 2}, {"block_4_6", 256, 256, 3, 2}};
+constexpr int MC_FUSED_MIN_PAIRS = 64;   // bf16: batches from this size on use the fused masked-A MC GEMM
 const char* P1 = "model_part1.";
 const char* P4 = "model_last_block_list.0.";
 
@@ -107,7 +108,7 @@ struct uahn_handle {
   float *W1m = nullptr, *b1m = nullptr, *W1u = nullptr, *b1u = nullptr;       // [5120][256] fp32 (k' order)
   ConvBf16Weights W1m_b, W1u_b;
   float *W2m = nullptr, *b2m = nullptr, *W2u = nullptr, *b2u = nullptr;
-  void* mcA = nullptr;    // fp32 mode: [2][cap][16][5120] masked features; bf16 mode: keep bits [2][cap][640][16] bytes
+  void* mcA = nullptr;    // [2][n][16][5120] masked features (fp32, small bf16 batches) or keep bits [2][n][640][16] bytes
   void* hid = nullptr;    // [2][cap][16][256] T
   float* Hb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // cumulative H after prior(0)/block1..3 ; [4] unused
   float* Htot = nullptr;
@@ -454,20 +455,28 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
   if ((rc = run_block<T>(h, B4, n, prev, curr, Hcur))) return rc;             // model_to_trace.py:261-263
   const T* feat = (const T*)B4.layers.back().out.p;
   const uint64_t seed = rng ? rng->seed : 0, first = rng ? rng->first_pair_index : 0;
-  if constexpr (sizeof(T) == 4) {
+  // bf16, large batches: the dropout expansion is fused into the GEMM's A producer and only the keep BITS (20 KB per
+  // pair) are staged.  Small batches (the batch-1 latency path) and fp32 mode materialise the masked features: with one
+  // or two M tiles the fused producer is a serial latency chain (80 K-stages per tile) and the plain GEMM, split over N
+  // tiles, finishes sooner.
+  const bool fused_mc = sizeof(T) == 2 && n >= MC_FUSED_MIN_PAIRS;
+  if (!fused_mc) {
     h->prof_begin(3);
     LAUNCH(launch_mc_expand<T>(n, feat, (T*)h->mcA, d_masks, seed, first, rng_dev, st));
     h->prof_end();
     h->prof_begin(2);
     for (int head = 0; head < 2; ++head) {
       ConvGeom g = dense_geom(n * MC, FC_IN, FC_HID, 1);
-      const float* a = (const float*)h->mcA + (size_t)head * n * MC * FC_IN;
-      float* o = (float*)h->hid + (size_t)head * n * MC * FC_HID;
-      LAUNCH(launch_conv_f32(a, head ? h->W1u : h->W1m, head ? h->b1u : h->b1m, o, g, st));
+      const T* a = (const T*)h->mcA + (size_t)head * n * MC * FC_IN;
+      T* o = (T*)h->hid + (size_t)head * n * MC * FC_HID;
+      if constexpr (sizeof(T) == 4) {
+        LAUNCH(launch_conv_f32((const float*)a, head ? h->W1u : h->W1m, head ? h->b1u : h->b1m, (float*)o, g, st));
+      } else {
+        LAUNCH(launch_conv_bf16(head ? h->W1u_b : h->W1m_b, a, head ? h->b1u : h->b1m, o, g, st));
+      }
     }
     h->prof_end();
   } else {
-    // bf16: the dropout expansion is fused into the GEMM's A producer; only the keep BITS (20 KB per pair) are staged
     h->prof_begin(3);
     LAUNCH(launch_mc_maskbits(n, (uint8_t*)h->mcA, d_masks, seed, first, rng_dev, st));
     h->prof_end();
@@ -563,7 +572,11 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
   if ((rc = build_head(h, w))) return bail(rc);
   const size_t cap = h->cap;
   uint8_t* p8 = nullptr;
-  if ((rc = dev_alloc(h, &p8, h->bf16 ? 2 * cap * (FC_IN / 8) * MC : 2 * cap * MC * FC_IN * h->es))) return bail(rc);
+  {
+    const size_t expand_pairs = h->bf16 ? std::min<size_t>(cap, MC_FUSED_MIN_PAIRS - 1) : cap;   // pairs on the expand path
+    const size_t bytes = std::max<size_t>(2 * expand_pairs * MC * FC_IN * h->es, h->bf16 ? 2 * cap * (FC_IN / 8) * MC : 0);
+    if ((rc = dev_alloc(h, &p8, bytes))) return bail(rc);
+  }
   h->mcA = p8;
   if ((rc = dev_alloc(h, &p8, 2 * cap * MC * FC_HID * h->es))) return bail(rc);
   h->hid = p8;

@@ -193,6 +193,22 @@ def test_philox_and_explicit_masks_agree(api, wfile, precision):
         assert np.array_equal(m0, m1) and np.array_equal(c0, c1)
 
 
+def test_fused_mc_gemm_matches_expand_path(api, wfile):
+    """bf16, n >= 64: the masked-A GEMM producer (keep bits, no materialised masks) vs the expand + GEMM path that small
+    batches take; Philox masks and explicit masks; a batch that leaves the last 128-row tile partly empty."""
+    n = 70
+    prev, curr, _, prior = S.tiled_batch(n, unique=6)
+    packed = np.stack([api.philox_keep_masks(5, 100 + i) for i in range(n)])
+    with api.Uahn(wfile, "prior3", precision="bf16", max_batch=n) as net:
+        m_big, c_big, _ = net.infer_batch(prev, curr, prior, seed=5, first_pair=100)          # fused, Philox bits
+        m_exp, c_exp, _ = net.infer_batch(prev, curr, prior, keep_masks=packed)               # fused, explicit masks
+        assert np.array_equal(m_big, m_exp) and np.array_equal(c_big, c_exp)
+        for lo in (0, 32, 64):                                                                # expand path, 6 pairs at a time
+            m6, c6, _ = net.infer_batch(prev[lo:lo + 6], curr[lo:lo + 6], prior[lo:lo + 6], seed=5, first_pair=100 + lo)
+            assert np.abs(m6 - m_big[lo:lo + 6]).max() < 2e-3, np.abs(m6 - m_big[lo:lo + 6]).max()
+            assert np.abs(c6 - c_big[lo:lo + 6]).max() <= 2e-3 * np.abs(c6).max()
+
+
 def test_sequence_submission_matches_pairwise_call(api, wfile):
     """uahn_submit_sequence: pair i = (frames[i], frames[i+1]), every frame uploaded once."""
     import torch as _t
