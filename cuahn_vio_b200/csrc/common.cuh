@@ -54,7 +54,10 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : v * LRELU_SLOPE; }
 
-// ---- Philox4x32-10 (host + device): the in-kernel MC-dropout mask source ------------------------------
+// ---- Philox4x32-7 (host + device): the in-kernel MC-dropout mask source ---------------------------------
+// 7 rounds is the smallest Crush-resistant Philox4x32 (Salmon et al., SC'11; 10 is the library default's safety
+// margin).  The masks cost 20 480 Philox blocks per pair, so the rounds are the run time of mc_maskbits_kernel.
+constexpr int PHILOX_ROUNDS = 7;
 struct Philox {
   static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
   __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
@@ -66,7 +69,7 @@ struct Philox {
                                              uint32_t out[4]) {
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < PHILOX_ROUNDS; ++r) {
       uint32_t h0, l0, h1, l1;
       mulhilo(M0, c0, h0, l0);
       mulhilo(M1, c2, h1, l1);

@@ -73,7 +73,7 @@ typedef struct uahn_config {
 } uahn_config;
 
 /* MC-dropout randomness (model_to_trace.py:222-235, 266-273).
- * keep_masks == NULL: masks are drawn in-kernel from Philox4x32-10 keyed by (seed, first_pair_index + i).
+ * keep_masks == NULL: masks are drawn in-kernel from Philox4x32-7 keyed by (seed, first_pair_index + i).
  * keep_masks != NULL: explicit replay; HOST (or device, for the *_device call) bytes, 1 = kept, 0 = dropped,
  *   laid out [pair][head(0=mean,1=uncertainty)][sample 0..15][5120 inputs, then 256 hidden], the 5120 axis
  *   in the reference's NCHW flatten order c*20 + h*5 + w.  Kept values are scaled by 1/0.95. */
