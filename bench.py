@@ -124,6 +124,11 @@ def reference_runner(variant: str = "prior3"):
     import numpy as np
     import torch
     from cuahn_vio_b200 import synthetic as S
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its ranks)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     name = {"prior3": "traced_model_3_blocks_using_prior.pt", "full": "traced_full_model.pt"}[variant]
     path = os.path.join(ROOT, "oracle", "_ref", name)
     prev, curr, _, prior = S.synthetic_batch(16)
@@ -211,6 +216,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
