@@ -23,7 +23,8 @@ EXPORTED_SYMBOLS = [
     "uahn_wait",
 ]
 PREPROC_SYMBOLS = ["uahn_undistort_init_maps", "uahn_set_undistort_maps", "uahn_load_raw_image", "uahn_stage_undistort"]
-EKF_SYMBOLS = ["uahn_ekf_prior_px", "uahn_ekf_update", "uahn_ekf_reset_offsets", "uahn_ekf_iekf_frame"]
+EKF_SYMBOLS = ["uahn_ekf_prior_px", "uahn_ekf_update", "uahn_ekf_reset_offsets", "uahn_ekf_iekf_frame",
+               "uahn_imu_select_readings", "uahn_imu_predict_and_compute", "uahn_imu_propagate"]
 
 
 class UahnError(RuntimeError):
@@ -51,6 +52,64 @@ class EkfState(C.Structure):
     def arrays(self):
         return (np.array(self.imu[:], np.float64), np.array([list(self.offset[c]) for c in range(4)], np.float64),
                 np.array(self.cov[:], np.float64).reshape(27, 27))
+
+
+class ImuSample(C.Structure):
+    _fields_ = [("t", C.c_double), ("wm", C.c_double * 3), ("am", C.c_double * 3)]
+
+
+class PropagatorConfig(C.Structure):
+    """uahn_propagator_config: camera extrinsics of the planar-homography corner dynamics + IMU noise."""
+    _fields_ = [("c_R_i", C.c_double * 9), ("i_t_i2c", C.c_double * 3), ("sigma_w", C.c_double), ("sigma_a", C.c_double),
+                ("sigma_wb", C.c_double), ("sigma_ab", C.c_double), ("gravity_mag", C.c_double), ("imu_avg", C.c_int)]
+
+    @classmethod
+    def make(cls, c_R_i, i_t_i2c, imu_avg: bool = True):
+        c = cls()
+        c.c_R_i[:] = [float(v) for v in np.asarray(c_R_i, np.float64).reshape(9)]
+        c.i_t_i2c[:] = [float(v) for v in np.asarray(i_t_i2c, np.float64).reshape(3)]
+        c.imu_avg = int(imu_avg)
+        return c
+
+
+def _imu_array(readings):
+    arr = (ImuSample * len(readings))()
+    for a, (t, wm, am) in zip(arr, readings):
+        a.t = float(t)
+        a.wm[:] = [float(v) for v in wm]
+        a.am[:] = [float(v) for v in am]
+    return arr
+
+
+def imu_select_readings(readings, time0: float, time1: float):
+    lib = load_library()
+    arr = _imu_array(readings)
+    out = (ImuSample * (len(readings) + 4))()
+    n = C.c_int(0)
+    rc = lib.uahn_imu_select_readings(arr, len(readings), float(time0), float(time1), out, len(out), C.byref(n))
+    if rc:
+        raise UahnError(f"uahn_imu_select_readings: error {rc}")
+    return [(o.t, np.array(o.wm[:]), np.array(o.am[:])) for o in out[:n.value]]
+
+
+def imu_predict_and_compute(cfg: "PropagatorConfig", state: "EkfState", minus, plus):
+    lib = load_library()
+    a = _imu_array([minus, plus])
+    F, Fw = np.empty((27, 27), np.float64), np.empty((27, 15), np.float64)
+    rc = lib.uahn_imu_predict_and_compute(C.byref(cfg), C.byref(state), C.byref(a[0]), C.byref(a[1]), _ptr(F), _ptr(Fw))
+    if rc:
+        raise UahnError(f"uahn_imu_predict_and_compute: error {rc}")
+    return F, Fw
+
+
+def imu_propagate(cfg: "PropagatorConfig", state: "EkfState", readings, time0: float, time1: float) -> int:
+    lib = load_library()
+    arr = _imu_array(readings)
+    n = C.c_int(0)
+    rc = lib.uahn_imu_propagate(C.byref(cfg), C.byref(state), arr, len(readings), float(time0), float(time1), C.byref(n))
+    if rc:
+        raise UahnError(f"uahn_imu_propagate: error {rc}")
+    return n.value
 
 
 class _Rng(C.Structure):
@@ -130,6 +189,12 @@ def load_library(path: str | None = None):
     lib.uahn_ekf_reset_offsets.restype = i
     lib.uahn_ekf_iekf_frame.argtypes = [vp, vp, ekf, i, dbl, i, i, C.POINTER(_Rng), vp, vp]
     lib.uahn_ekf_iekf_frame.restype = i
+    lib.uahn_imu_select_readings.argtypes = [vp, i, dbl, dbl, vp, i, vp]
+    lib.uahn_imu_select_readings.restype = i
+    lib.uahn_imu_predict_and_compute.argtypes = [vp, ekf, vp, vp, vp, vp]
+    lib.uahn_imu_predict_and_compute.restype = i
+    lib.uahn_imu_propagate.argtypes = [vp, ekf, vp, i, dbl, dbl, vp]
+    lib.uahn_imu_propagate.restype = i
     if path is None:
         _lib = lib
     return lib

@@ -54,6 +54,41 @@ UAHN_API int uahn_ekf_reset_offsets(uahn_ekf_state* s);
 UAHN_API int uahn_ekf_iekf_frame(uahn_handle* h, uahn_handle* h_iter, uahn_ekf_state* s, int max_iter, double K_net_Cov,
                         int min_images, int use_measurement, const uahn_rng* rng, double* mean_px8, double* cov_px64);
 
+/* ---- IMU propagation producing the prior ---------------------------------------------------
+ * Replaces Propagator::select_imu_readings / interpolate_data (cuahn/src/state/Propagator.cpp:80-180, Propagator.h:179-189),
+ * Propagator::predict_and_compute + predict_mean_discrete (Propagator.cpp:183-363) and StateHelper::propagate_Cov
+ * (StateHelper.cpp:28-32): the planar-homography corner dynamics that turn IMU readings into the propagated 4-point
+ * offsets (the network's prior) and their covariance. */
+typedef struct uahn_imu_sample {
+  double t;
+  double wm[3]; /* gyroscope, rad/s  */
+  double am[3]; /* accelerometer, m/s^2 */
+} uahn_imu_sample;
+
+typedef struct uahn_propagator_config {
+  double c_R_i[9];    /* State::c_RotMtrx_i, row-major (rotation block of the camera extrinsics, State.cpp:93-96) */
+  double i_t_i2c[3];  /* State::i_tVec_i2c                                                                           */
+  double sigma_w, sigma_a, sigma_wb, sigma_ab; /* NoiseManager (Propagator.h:50-71); <= 0 selects the reference defaults */
+  double gravity_mag; /* 9.81 (Propagator.h:100); <= 0 selects it                                                    */
+  int imu_avg;        /* StateOptions::imu_avg (default true, StateOptions.h:39)                                     */
+} uahn_propagator_config;
+
+/* select_imu_readings: the readings that cover [time0, time1], first and last interpolated onto the interval ends.
+ * Writes at most `capacity` samples to `out`, their count to *n_out (fewer than 2 = cannot propagate). */
+UAHN_API int uahn_imu_select_readings(const uahn_imu_sample* imu, int n, double time0, double time1, uahn_imu_sample* out,
+                             int capacity, int* n_out);
+
+/* predict_and_compute for one IMU interval: advances the state mean (IMU value and the four offsets) and returns the
+ * state-transition Jacobian F (27x27) and noise Jacobian Fw (27x15), row-major.  The covariance is NOT touched. */
+UAHN_API int uahn_imu_predict_and_compute(const uahn_propagator_config* cfg, uahn_ekf_state* s, const uahn_imu_sample* minus,
+                                 const uahn_imu_sample* plus, double* F, double* Fw);
+
+/* propagate_with_imu (Propagator.cpp:28-79) between two (already time-offset-corrected) instants: select readings,
+ * then for every interval predict_and_compute + P <- F P F^T + Fw Q Fw^T.  Returns the number of intervals integrated
+ * in *n_intervals (optional). */
+UAHN_API int uahn_imu_propagate(const uahn_propagator_config* cfg, uahn_ekf_state* s, const uahn_imu_sample* imu, int n,
+                       double time0, double time1, int* n_intervals);
+
 #ifdef __cplusplus
 }
 #endif
