@@ -40,8 +40,11 @@ constexpr int B1_STAGES = 4, B2_STAGES = 10;         // 7 taps packed in pairs; 
 constexpr int BSTAGE = 64 * 128;                     // N = 64 rows x 128 B
 constexpr int PLANE_ROWS = 18;                       // t = 0..15 written, +2 rows read only by dummy M rows
 constexpr int PLANE_BYTES = PLANE_ROWS * 8 * 128;    // 18 432
-constexpr int SMEM_BYTES = 1024 + 2 * IN_BYTES + B1_STAGES * BSTAGE + B2_STAGES * BSTAGE + 2 * PLANE_BYTES + 2 * 64 * 4 +
-                           32 * 8;
+constexpr int smem_bytes(bool pair) {   // pair: half of B per CTA, the conv-2 operand planes double-buffered
+  return 1024 + 2 * IN_BYTES + (B1_STAGES + B2_STAGES) * (pair ? BSTAGE / 2 : BSTAGE) + (pair ? 2 : 1) * 2 * PLANE_BYTES +
+         2 * 64 * 4 + 32 * 8;
+}
+constexpr int SMEM_BYTES = smem_bytes(false) > smem_bytes(true) ? smem_bytes(false) : smem_bytes(true);
 
 #ifndef UAHN_FF_PROFILE
 #define UAHN_FF_PROFILE 0
@@ -64,20 +67,29 @@ struct FusedParams {
   unsigned long long magic_tiles, magic_tx;
 };
 
-// C1: conv-1 output channels (8 or 16); KS2B: k-steps of conv-2 chunk 1 (2 for block 4, 3 for block 3)
-template <int C1, int KS2B>
+// C1: conv-1 output channels (8 or 16); KS2B: k-steps of conv-2 chunk 1 (2 for block 4, 3 for block 3).
+// PAIR: launched as clusters of two CTAs that share every UMMA (tcgen05.mma.cta_group::2, M = 256): each CTA keeps its
+// own tile stream, input planes, D1 -> planes epilogue and output, but holds only HALF of the resident B operands (32 of
+// the 64 N rows) — the tensor core's operand fetch from shared memory, which bounds this kernel, drops from 6 KB to 5 KB
+// per CTA and MMA.  Only the leader (cluster rank 0) issues MMAs; its hand-off barriers count arrivals from both CTAs.
+template <int C1, int KS2B, bool PAIR>
 __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                           const __grid_constant__ FusedParams p) {
   constexpr int G1 = 64 / C1;                        // conv-1 pixels per group
+  constexpr int BST = PAIR ? BSTAGE / 2 : BSTAGE;    // bytes of one resident B stage in THIS CTA
+  constexpr int NCTA = PAIR ? 2 : 1;
+  constexpr int NPL = PAIR ? 2 : 1;                  // buffers of the conv-2 operand planes (the pair has the room)
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const bool cta_leader = crank == 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sIn = smem;                                             // conv-1 input plane, double-buffered
   uint8_t* sB1 = sIn + 2 * IN_BYTES;
-  uint8_t* sB2 = sB1 + B1_STAGES * BSTAGE;
-  uint8_t* sPl = sB2 + B2_STAGES * BSTAGE;                         // [2 parities][PLANE_BYTES]
-  float* sBias = reinterpret_cast<float*>(sPl + 2 * PLANE_BYTES);  // [2][64]
+  uint8_t* sB2 = sB1 + B1_STAGES * BST;
+  uint8_t* sPl = sB2 + B2_STAGES * BST;                            // [2 parities][PLANE_BYTES]
+  float* sBias = reinterpret_cast<float*>(sPl + NPL * 2 * PLANE_BYTES);  // [2][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 128);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
@@ -85,25 +97,31 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
   const int tiles_per_img = p.TX * p.TY;
   const int total_tiles = p.n_img * tiles_per_img;
 
-  // bars: 0-1 in_full[buf], 2 bres, 3-6 d1_full[buf][jt], 7-10 d1_empty[buf][jt], 11 planes_full, 12 d2_full,
-  //       13 d2_empty, 14-15 in_empty[buf]
-  constexpr int B_IN_FULL = 0, B_RES = 2, B_D1_FULL = 3, B_D1_EMPTY = 7, B_PL_FULL = 11, B_D2_FULL = 12,
-                B_D2_EMPTY = 13, B_IN_EMPTY = 14;
+  // bars: 0-1 in_full[buf], 2 bres, 3-6 d1_full[buf][jt], 7-10 d1_empty[buf][jt], 11 d2_full, 12 d2_empty,
+  //       13-14 in_empty[buf], 15-16 planes_full[pb], 17-18 planes_empty[pb]
+  constexpr int B_IN_FULL = 0, B_RES = 2, B_D1_FULL = 3, B_D1_EMPTY = 7, B_D2_FULL = 11, B_D2_EMPTY = 12, B_IN_EMPTY = 13,
+                B_PL_FULL = 15, B_PL_EMPTY = 17;
   constexpr uint32_t TMEM_COLS = 512;                    // D1: 2 buffers x 2 row tiles x 64 columns; D2: 64 columns at 256
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_IN_FULL + i), 1); mbar_init(BAR(B_IN_EMPTY + i), 1); }
       mbar_init(BAR(B_RES), 1);
-      for (int i = 0; i < 4; ++i) { mbar_init(BAR(B_D1_FULL + i), 1); mbar_init(BAR(B_D1_EMPTY + i), FF_EPI1_WARPS); }
-      mbar_init(BAR(B_PL_FULL), FF_EPI1_WARPS);
-      mbar_init(BAR(B_D2_FULL), 1); mbar_init(BAR(B_D2_EMPTY), FF_EPI2_WARPS);
+      for (int i = 0; i < 4; ++i) { mbar_init(BAR(B_D1_FULL + i), 1); mbar_init(BAR(B_D1_EMPTY + i), NCTA * FF_EPI1_WARPS); }
+      for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_PL_FULL + i), NCTA * FF_EPI1_WARPS); mbar_init(BAR(B_PL_EMPTY + i), 1); }
+      mbar_init(BAR(B_D2_FULL), 1); mbar_init(BAR(B_D2_EMPTY), NCTA * FF_EPI2_WARPS);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int i = tid; i < 64; i += FF_THREADS) { sBias[i] = p.bias1_x[i]; sBias[64 + i] = p.bias2_x[i]; }
   tc_fence_before();
@@ -129,17 +147,24 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
     }
     tmem_st_wait();
   }
+  if (warp == 0 && lane == 0) {
+    // resident B operands: all 64 N rows of every stage, or this CTA's 32 rows of them (PAIR)
+    tma_prefetch_desc(&tmap);
+    mbar_arrive_expect_tx(BAR(B_RES), (uint32_t)((B1_STAGES + B2_STAGES) * BST));
+    for (int s = 0; s < B1_STAGES; ++s)
+      bulk_g2s(smem_u32(sB1 + s * BST), p.b1_image + (size_t)s * BSTAGE + (size_t)crank * BST, BST, BAR(B_RES));
+    for (int s = 0; s < B2_STAGES; ++s)
+      bulk_g2s(smem_u32(sB2 + s * BST), p.b2_image + (size_t)s * BSTAGE + (size_t)crank * BST, BST, BAR(B_RES));
+    if (PAIR) mbar_wait(BAR(B_RES), 0);        // the leader's MMAs read the peer's half: resident before the cluster sync
+  }
+  __syncwarp();                                // barrier.cluster is .aligned: every warp arrives converged
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      tma_prefetch_desc(&tmap);
-      mbar_arrive_expect_tx(BAR(B_RES), (uint32_t)((B1_STAGES + B2_STAGES) * BSTAGE));
-      for (int s = 0; s < B1_STAGES; ++s) bulk_g2s(smem_u32(sB1 + s * BSTAGE), p.b1_image + (size_t)s * BSTAGE, BSTAGE, BAR(B_RES));
-      for (int s = 0; s < B2_STAGES; ++s) bulk_g2s(smem_u32(sB2 + s * BSTAGE), p.b2_image + (size_t)s * BSTAGE, BSTAGE, BAR(B_RES));
       long long pw = 0;
       const long long pbeg = ff_clock();
       for (int k = 0; k < my_tiles; ++k) {
@@ -150,35 +175,45 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         const int ib = k & 1;
         mbar_wait(BAR(B_IN_EMPTY + ib), ((k >> 1) & 1) ^ 1);  // conv-1 MMAs of tile k-2 have read this buffer
         pw += ff_clock() - t0;
-        mbar_arrive_expect_tx(BAR(B_IN_FULL + ib), IN_BYTES);
-        tma_load_4d(smem_u32(sIn + ib * IN_BYTES), &tmap, 0, 7 * tx, 28 * ty, img, BAR(B_IN_FULL + ib));
+        if (PAIR) {   // both CTAs' planes complete on the leader's barrier, which the leader arms for both
+          if (cta_leader) mbar_arrive_expect_tx(BAR(B_IN_FULL + ib), 2 * IN_BYTES);
+          tma_load_4d_pair(smem_u32(sIn + ib * IN_BYTES), &tmap, 0, 7 * tx, 28 * ty, img, BAR(B_IN_FULL + ib));
+        } else {
+          mbar_arrive_expect_tx(BAR(B_IN_FULL + ib), IN_BYTES);
+          tma_load_4d(smem_u32(sIn + ib * IN_BYTES), &tmap, 0, 7 * tx, 28 * ty, img, BAR(B_IN_FULL + ib));
+        }
       }
       if (p.dbg) { p.dbg[blockIdx.x * 24 + 0] = pw; p.dbg[blockIdx.x * 24 + 1] = ff_clock() - pbeg; }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && cta_leader) {
+    // ===================== MMA issuer (the leader CTA of a pair issues for both) =====================
     // Issue order: conv1(0), then per tile k: conv1(k+1), conv2(k).  conv 2 of tile k has to wait for the conv-1
     // epilogue of tile k (TMEM -> registers -> planes); with conv 1 of the NEXT tile queued in front of it the tensor
     // pipe works through that wait instead of idling (D1 is double-buffered in TMEM for this).
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+    constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, 64);
     constexpr uint64_t DESC_HI = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id) {
+      if (PAIR) tc_mma_bf16_pair(d, a, b, id, 1u); else tc_mma_bf16(d, a, b, id, 1u);   // accumulators hold the bias
+    };
+    auto commit = [](uint32_t bar) { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); };
+    auto wait = [](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t in16 = (smem_u32(sIn) & 0x3FFFFu) >> 4, b1_16 = (smem_u32(sB1) & 0x3FFFFu) >> 4;
     const uint32_t b2_16 = (smem_u32(sB2) & 0x3FFFFu) >> 4, pl16 = (smem_u32(sPl) & 0x3FFFFu) >> 4;
-    mbar_wait(BAR(B_RES), 0);
+    if (!PAIR) mbar_wait(BAR(B_RES), 0);
     long long mw_in = 0, mw_d1e = 0, mw_pl = 0, mw_d2e = 0, tq;
     const long long mbeg = ff_clock();
     const bool leader = elect_one();
     auto conv1 = [&](int k) {
       const int buf = k & 1;
       tq = ff_clock();
-      mbar_wait(BAR(B_IN_FULL + buf), (k >> 1) & 1);
+      wait(BAR(B_IN_FULL + buf), (k >> 1) & 1);
       mw_in += ff_clock() - tq;
       tc_fence_after();
 #pragma unroll
       for (int jt = 0; jt < 2; ++jt) {
         tq = ff_clock();
-        mbar_wait(BAR(B_D1_EMPTY + buf * 2 + jt), ((k >> 1) & 1) ^ 1);   // epilogue has drained this D1 of tile k-2
+        wait(BAR(B_D1_EMPTY + buf * 2 + jt), ((k >> 1) & 1) ^ 1);        // epilogue has drained this D1 of tile k-2
         mw_d1e += ff_clock() - tq;
         tc_fence_after();
         if (leader) {
@@ -187,12 +222,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
               const uint32_t alo = in16 + (uint32_t)(buf * (IN_BYTES / 16) + (16 * jt + ky) * (8 * 128 / 16) + kk * 2);
-              const uint32_t blo = b1_16 + (uint32_t)((ky >> 1) * (BSTAGE / 16) + (ky & 1) * 4 + kk * 2);
-              tc_mma_bf16(tmem_u + (uint32_t)(buf * 128 + jt * 64), DESC_HI | (uint64_t)alo, DESC_HI | (uint64_t)blo, idesc,
-                          1u);                                // D1 was pre-loaded with the bias
+              const uint32_t blo = b1_16 + (uint32_t)((ky >> 1) * (BST / 16) + (ky & 1) * 4 + kk * 2);
+              mma(tmem_u + (uint32_t)(buf * 128 + jt * 64), DESC_HI | (uint64_t)alo, DESC_HI | (uint64_t)blo, idesc);
             }
-          tc_commit(BAR(B_D1_FULL + buf * 2 + jt));
-          if (jt == 1) tc_commit(BAR(B_IN_EMPTY + buf));      // this input buffer may be refilled
+          commit(BAR(B_D1_FULL + buf * 2 + jt));
+          if (jt == 1) commit(BAR(B_IN_EMPTY + buf));         // this input buffer may be refilled
         }
         __syncwarp();
       }
@@ -201,11 +235,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
     for (int k = 0; k < my_tiles; ++k) {
       if (k + 1 < my_tiles) conv1(k + 1);
       // ---- conv 2: 5 taps x (4 + KS2B) k-steps on the planes written by the conv-1 epilogue ----
+      const int pb = k % NPL;
       tq = ff_clock();
-      mbar_wait(BAR(B_PL_FULL), k & 1);
+      wait(BAR(B_PL_FULL + pb), (k / NPL) & 1);
       mw_pl += ff_clock() - tq;
       tq = ff_clock();
-      mbar_wait(BAR(B_D2_EMPTY), (k & 1) ^ 1);                // D2 of the previous tile has been read
+      wait(BAR(B_D2_EMPTY), (k & 1) ^ 1);                     // D2 of the previous tile has been read
       mw_d2e += ff_clock() - tq;
       tc_fence_after();
       if (leader) {
@@ -216,12 +251,13 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
           for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int kk = 0; kk < (c == 0 ? 4 : KS2B); ++kk) {
-              const uint32_t alo = pl16 + (uint32_t)(rho * (PLANE_BYTES / 16) + (a * 8 + c) * (128 / 16) + kk * 2);
-              const uint32_t blo = b2_16 + (uint32_t)((ky * 2 + c) * (BSTAGE / 16) + kk * 2);
-              tc_mma_bf16(tmem_u + 256u, DESC_HI | (uint64_t)alo, DESC_HI | (uint64_t)blo, idesc, 1u);
+              const uint32_t alo = pl16 + (uint32_t)((pb * 2 + rho) * (PLANE_BYTES / 16) + (a * 8 + c) * (128 / 16) + kk * 2);
+              const uint32_t blo = b2_16 + (uint32_t)((ky * 2 + c) * (BST / 16) + kk * 2);
+              mma(tmem_u + 256u, DESC_HI | (uint64_t)alo, DESC_HI | (uint64_t)blo, idesc);
             }
         }
-        tc_commit(BAR(B_D2_FULL));                            // also: the planes may be rewritten
+        commit(BAR(B_D2_FULL));
+        commit(BAR(B_PL_EMPTY + pb));                         // these planes may be rewritten
       }
       __syncwarp();
     }
@@ -230,8 +266,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
       d[2] = mw_in; d[3] = mw_d1e; d[4] = mw_pl; d[5] = mw_d2e; d[6] = ff_clock() - mbeg;
     }
     tc_fence_before();
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue warps (2..17) =====================
+    // arrivals on the barriers the MMA issuer waits on go to the leader CTA of the pair
+    auto arrive_mma = [](uint32_t bar) { if (PAIR) mbar_arrive_leader(bar); else mbar_arrive(bar); };
     const int m = q * 32 + lane;                              // accumulator row
     // tile coordinates advance incrementally (no divisions in the loop)
     const int step_img = (int)gridDim.x / tiles_per_img, step_rem = (int)gridDim.x - step_img * tiles_per_img;
@@ -263,7 +301,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         const int y0 = 28 * ty - 2, x0 = G1 * 7 * tx - 2;     // first conv-1 row / pixel of the tile region
         // conv 2's zero padding: conv-1 outputs outside the image must be stored as zeros (border tiles only)
         const bool border = y0 < 0 || y0 + 31 >= p.H1 || x0 < 0 || x0 + G1 * 8 - 1 >= p.W1;
-        if (k >= 1) mbar_wait(BAR(B_D2_FULL), (k - 1) & 1);   // conv 2 of tile k-1 has read the planes
+        const int pb = k % NPL;
+        mbar_wait(BAR(B_PL_EMPTY + pb), ((k / NPL) & 1) ^ 1);   // conv 2 of tile k - NPL has read these planes
         lap(0);
 #pragma unroll
         for (int jt = 0; jt < 2; ++jt) {
@@ -290,12 +329,13 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
           lap(5);
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            st_shared_v4(prow[jt] + pch[c], packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+            st_shared_v4(prow[jt] + (uint32_t)(pb * 2 * PLANE_BYTES) + pch[c], packed[4 * c], packed[4 * c + 1], packed[4 * c + 2],
+                         packed[4 * c + 3]);
           lap(2);
         }
         fence_proxy_async();                                  // generic-proxy writes -> visible to the UMMA reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_PL_FULL));
+        if (lane == 0) arrive_mma(BAR(B_PL_FULL + pb));
         // off the critical path: re-arm both D1 tiles with the bias and hand them back to the MMA warp
 #pragma unroll
         for (int jt = 0; jt < 2; ++jt) {
@@ -305,7 +345,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(BAR(B_D1_EMPTY + buf * 2)); mbar_arrive(BAR(B_D1_EMPTY + buf * 2 + 1)); }
+        if (lane == 0) { arrive_mma(BAR(B_D1_EMPTY + buf * 2)); arrive_mma(BAR(B_D1_EMPTY + buf * 2 + 1)); }
         rem += step_rem; img += step_img;
         if (rem >= tiles_per_img) { rem -= tiles_per_img; ++img; }
         lap(3);
@@ -328,7 +368,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_D2_EMPTY));
+        if (lane == 0) arrive_mma(BAR(B_D2_EMPTY));
         lap(1);
         uint32_t packed[16];
 #pragma unroll
@@ -352,10 +392,13 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
       if (warp == 2) { d[12] = laps[4]; d[13] = laps[5]; }
     }
   }
-  __syncthreads();
+  __syncwarp();
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // (PAIR: the peer's shared memory and TMEM are in use until the leader is done)
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -473,22 +516,31 @@ cudaError_t launch_conv_fused(const FusedPlan& plan, void* out, const ConvGeom& 
   if (debug) cudaMemsetAsync(d_dbg, 0, 24 * 8 * 1024, st);
   p.dbg = debug ? d_dbg : nullptr;
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(plan.tmap);
-  static bool attr8 = false, attr16 = false;
-  if (plan.C1 == 8) {
-    if (!attr8) {
-      cudaError_t e = cudaFuncSetAttribute(conv_fused_front_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-      if (e != cudaSuccess) return e;
-      attr8 = true;
-    }
-    conv_fused_front_kernel<8, 2><<<grid, FF_THREADS, SMEM_BYTES, st>>>(*tm, p);
-  } else {
-    if (!attr16) {
-      cudaError_t e = cudaFuncSetAttribute(conv_fused_front_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-      if (e != cudaSuccess) return e;
-      attr16 = true;
-    }
-    conv_fused_front_kernel<16, 3><<<grid, FF_THREADS, SMEM_BYTES, st>>>(*tm, p);
-  }
+  // CTA pairs (cta_group::2) need an even grid and an even tile count (tiles per image are 48 / 24: always even)
+  static const bool want_pair = getenv("UAHN_FF_NO_PAIR") == nullptr;
+  const bool pair = want_pair && grid >= 2 && tiles % 2 == 0;
+  auto launch = [&](auto kern, bool use_pair) -> cudaError_t {
+    const int smem = smem_bytes(use_pair);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(use_pair ? (grid & ~1) : grid);
+    cfg.blockDim = dim3(FF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = use_pair ? 2 : 1;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, *tm, p);
+  };
+  cudaError_t lerr;
+  if (plan.C1 == 8) lerr = pair ? launch(conv_fused_front_kernel<8, 2, true>, true) : launch(conv_fused_front_kernel<8, 2, false>, false);
+  else lerr = pair ? launch(conv_fused_front_kernel<16, 3, true>, true) : launch(conv_fused_front_kernel<16, 3, false>, false);
+  if (lerr != cudaSuccess) return lerr;
   if (debug) {
     std::vector<unsigned long long> h(24 * grid);
     cudaStreamSynchronize(st);

@@ -133,6 +133,58 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
   return v;
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster share one UMMA of M = 256, each supplying its 128 rows of A and
+// half of the N rows of B.  Barriers the issuing (leader, rank 0) CTA waits on live in the leader's shared memory; the
+// peer reaches them through the shared::cluster window: clearing bit 24 of a shared address selects the even CTA of
+// the pair (the same convention CUTLASS uses for its 2-SM kernels).
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at this shared-memory offset in the LEADER CTA of the pair.  Default (CTA-scope release)
+// semantics, like CUTLASS's ClusterBarrier::arrive(cta_id): the data the signal protects never leaves this CTA — its
+// own tensor core reads its shared memory / TMEM — and has been completed by fence.proxy.async / tcgen05.wait::st
+// before the arrive; a cluster-scope release costs ~1000 cycles per arrive here.
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on the same-offset barrier of BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO = 1 (unused),
 // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -171,6 +223,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tma
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
       ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+// the 2-SM form: data lands in THIS CTA's shared memory, the completion bytes are signalled on the leader's barrier
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3,
+                                                 uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar & PEER_BIT_MASK)
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
