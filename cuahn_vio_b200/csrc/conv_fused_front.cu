@@ -51,6 +51,13 @@ constexpr int SMEM_BYTES = smem_bytes(false) > smem_bytes(true) ? smem_bytes(fal
 #endif
 __device__ __forceinline__ long long ff_clock() { return UAHN_FF_PROFILE ? clock64() : 0ll; }
 
+// event trace of a few tiles of CTAs 0/1 (UAHN_FF_PROFILE only): TR(role, k, event)
+#define FF_TR(role, k, ev)                                                                                 \
+  do {                                                                                                     \
+    if (UAHN_FF_PROFILE && p.dbg && blockIdx.x < 2 && (k) >= 40 && (k) < 48)                                \
+      p.dbg[24 * 1024 + ((role) * 8 + ((k) - 40)) * 8 + (ev)] = (unsigned long long)clock64();             \
+  } while (0)
+
 struct FusedParams {
   unsigned long long* dbg;   // optional [grid][24] cycle counters (-DUAHN_FF_PROFILE=1 + UAHN_FF_DEBUG)
   const uint8_t* b1_image;
@@ -206,6 +213,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
     const bool leader = elect_one();
     auto conv1 = [&](int k) {
       const int buf = k & 1;
+      if (lane == 0) FF_TR(0, k, 0);                        // conv1(k) issue starts
       tq = ff_clock();
       wait(BAR(B_IN_FULL + buf), (k >> 1) & 1);
       mw_in += ff_clock() - tq;
@@ -230,6 +238,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         }
         __syncwarp();
       }
+      if (lane == 0) FF_TR(0, k, 1);                        // conv1(k) issued
     };
     if (my_tiles > 0) conv1(0);
     for (int k = 0; k < my_tiles; ++k) {
@@ -237,7 +246,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
       // ---- conv 2: 5 taps x (4 + KS2B) k-steps on the planes written by the conv-1 epilogue ----
       const int pb = k % NPL;
       tq = ff_clock();
+      if (lane == 0) FF_TR(0, k, 2);                        // waiting planes_full(k)
       wait(BAR(B_PL_FULL + pb), (k / NPL) & 1);
+      if (lane == 0) FF_TR(0, k, 3);                        // planes_full(k) seen
       mw_pl += ff_clock() - tq;
       tq = ff_clock();
       wait(BAR(B_D2_EMPTY), (k & 1) ^ 1);                     // D2 of the previous tile has been read
@@ -260,6 +271,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         commit(BAR(B_PL_EMPTY + pb));                         // these planes may be rewritten
       }
       __syncwarp();
+      if (lane == 0) FF_TR(0, k, 4);                        // conv2(k) issued
     }
     if (p.dbg && lane == 0) {
       unsigned long long* d = p.dbg + blockIdx.x * 24;
@@ -302,11 +314,14 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         // conv 2's zero padding: conv-1 outputs outside the image must be stored as zeros (border tiles only)
         const bool border = y0 < 0 || y0 + 31 >= p.H1 || x0 < 0 || x0 + G1 * 8 - 1 >= p.W1;
         const int pb = k % NPL;
+        if (warp == 2 && lane == 0) FF_TR(1 + blockIdx.x, k, 0);
         mbar_wait(BAR(B_PL_EMPTY + pb), ((k / NPL) & 1) ^ 1);   // conv 2 of tile k - NPL has read these planes
+        if (warp == 2 && lane == 0) FF_TR(1 + blockIdx.x, k, 1);
         lap(0);
 #pragma unroll
         for (int jt = 0; jt < 2; ++jt) {
           mbar_wait(BAR(B_D1_FULL + buf * 2 + jt), (k >> 1) & 1);
+          if (warp == 2 && lane == 0) FF_TR(1 + blockIdx.x, k, 2 + jt);
           lap(1);
           tc_fence_after();
           uint32_t r[32];
@@ -336,6 +351,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         fence_proxy_async();                                  // generic-proxy writes -> visible to the UMMA reads
         __syncwarp();
         if (lane == 0) arrive_mma(BAR(B_PL_FULL + pb));
+        if (warp == 2 && lane == 0) FF_TR(1 + blockIdx.x, k, 4);
         // off the critical path: re-arm both D1 tiles with the bias and hand them back to the MMA warp
 #pragma unroll
         for (int jt = 0; jt < 2; ++jt) {
@@ -346,6 +362,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { arrive_mma(BAR(B_D1_EMPTY + buf * 2)); arrive_mma(BAR(B_D1_EMPTY + buf * 2 + 1)); }
+        if (warp == 2 && lane == 0) FF_TR(1 + blockIdx.x, k, 5);
         rem += step_rem; img += step_img;
         if (rem >= tiles_per_img) { rem -= tiles_per_img; ++img; }
         lap(3);
@@ -358,6 +375,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
       for (int k = 0; k < my_tiles; ++k) {
         const int ty = (int)(((uint32_t)rem * mtx) >> 16), tx = rem - ty * p.TX;
         mbar_wait(BAR(B_D2_FULL), k & 1);
+        if (warp == 10 && lane == 0 && blockIdx.x == 0) FF_TR(3, k, 0);
         lap(0);
         tc_fence_after();
         uint32_t r[32];
@@ -369,6 +387,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_mma(BAR(B_D2_EMPTY));
+        if (warp == 10 && lane == 0 && blockIdx.x == 0) FF_TR(3, k, 1);
         lap(1);
         uint32_t packed[16];
 #pragma unroll
@@ -512,8 +531,8 @@ cudaError_t launch_conv_fused(const FusedPlan& plan, void* out, const ConvGeom& 
   const int grid = std::min(tiles, num_sms);
   static unsigned long long* d_dbg = nullptr;
   const bool debug = UAHN_FF_PROFILE && getenv("UAHN_FF_DEBUG") != nullptr;
-  if (debug && !d_dbg) cudaMalloc(&d_dbg, 24 * 8 * 1024);
-  if (debug) cudaMemsetAsync(d_dbg, 0, 24 * 8 * 1024, st);
+  if (debug && !d_dbg) cudaMalloc(&d_dbg, 24 * 8 * 1024 + 8 * 4096);
+  if (debug) cudaMemsetAsync(d_dbg, 0, 24 * 8 * 1024 + 8 * 4096, st);
   p.dbg = debug ? d_dbg : nullptr;
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(plan.tmap);
   // CTA pairs (cta_group::2) need an even grid and an even tile count (tiles per image are 48 / 24: always even)
@@ -545,14 +564,31 @@ cudaError_t launch_conv_fused(const FusedPlan& plan, void* out, const ConvGeom& 
     std::vector<unsigned long long> h(24 * grid);
     cudaStreamSynchronize(st);
     cudaMemcpy(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
-    double a[24] = {0};
     const double tl = (double)tiles / grid;
-    for (int i = 0; i < grid; ++i) for (int j = 0; j < 24; ++j) a[j] += (double)h[i * 24 + j] / grid / tl;
-    fprintf(stderr, "[uahn-ff] C1=%d tiles/CTA=%.1f per tile (cycles): producer wait_in_empty %.0f of %.0f | mma wait in_full %.0f d1_empty %.0f planes_full %.0f d2_empty %.0f of %.0f\n",
-            plan.C1, tl, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
-    fprintf(stderr, "[uahn-ff]   epi1(w2): wait planes free %.0f | wait d1_full %.0f | ld+pack+sts %.0f | fence+arrive+rearm %.0f | total %.0f   epi2(w10): wait d2_full %.0f | drain %.0f | pack+store %.0f | total %.0f\n",
-            a[8], a[9], a[10], a[11], a[12], a[14], a[15], a[16], a[18]);
-    fprintf(stderr, "[uahn-ff]   epi1 detail: tmem ld %.0f | pack %.0f | sts %.0f\n", a[20], a[21], a[10]);
+    for (int par = 0; par < 2; ++par) {       // even (leader) and odd (peer) CTAs separately
+      double a[24] = {0};
+      int cnt = 0;
+      for (int i = par; i < grid; i += 2, ++cnt) for (int j = 0; j < 24; ++j) a[j] += (double)h[i * 24 + j] / tl;
+      for (int j = 0; j < 24; ++j) a[j] /= cnt;
+      fprintf(stderr, "[uahn-ff] C1=%d %s CTAs, per tile (cycles): producer wait_in_empty %.0f of %.0f | mma wait in_full %.0f d1_empty %.0f planes_full %.0f d2_empty %.0f of %.0f\n",
+              plan.C1, par ? "odd " : "even", a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+      fprintf(stderr, "[uahn-ff]   epi1(w2): wait planes free %.0f | wait d1_full %.0f | tmem ld %.0f | pack %.0f | sts %.0f | fence+arrive+rearm %.0f | total %.0f   epi2(w10): wait d2_full %.0f | drain %.0f | pack+store %.0f | total %.0f\n",
+              a[8], a[9], a[20], a[21], a[10], a[11], a[12], a[14], a[15], a[16], a[18]);
+    }
+    {
+      std::vector<unsigned long long> tr(4 * 8 * 8);
+      cudaMemcpy(tr.data(), d_dbg + 24 * 1024, tr.size() * 8, cudaMemcpyDeviceToHost);
+      const unsigned long long t0 = tr[0];
+      if (t0)
+        for (int k = 0; k < 8; ++k) {
+          fprintf(stderr, "[uahn-ff-trace] tile %d:", 40 + k);
+          for (int role = 0; role < 4; ++role) {
+            fprintf(stderr, "  r%d", role);
+            for (int ev = 0; ev < 6; ++ev) fprintf(stderr, " %lld", (long long)(tr[(role * 8 + k) * 8 + ev] ? tr[(role * 8 + k) * 8 + ev] - t0 : 0));
+          }
+          fprintf(stderr, "\n");
+        }
+    }
   }
   return cudaGetLastError();
 }
