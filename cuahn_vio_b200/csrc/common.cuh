@@ -45,6 +45,33 @@ struct ConvGeom {
   int act;               // 1: LeakyReLU(0.1), 0: identity
 };
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// Every kernel of the forward is launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next
+// kernel's CTAs may become resident and run their prologue (barrier init, TMEM allocation, weight loads) while the
+// previous kernel drains, and block in pdl_wait() until its memory is visible.  Nothing produced by an earlier
+// kernel may be read, and nothing may be written to global memory, before pdl_wait().  Used on the small-batch latency path only (engine.cu: pdl_select);
+// UAHN_NO_PDL=1 disables it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+bool pdl_enabled();   // engine.cu: switched per forward() call by the batch size
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }

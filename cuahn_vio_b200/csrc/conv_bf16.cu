@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // everything above touched only shared memory, TMEM and weights
+  pdl_launch_dependents();    // persistent grid: all CTAs are resident, the next kernel may start its prologue
 
   if (MC_A && warp < 4) {
     // ===================== masked-feature producer (MC-dropout GEMM) =====================
@@ -368,8 +370,7 @@ cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st) {
     attr = smem;
   }
   const int tiles = p.m_tiles * p.n_tiles;
-  conv_igemm_bf16_kernel<BN, STAGES, B_RES, MC_A><<<std::min(tiles, num_sms), IG_THREADS, smem, st>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(conv_igemm_bf16_kernel<BN, STAGES, B_RES, MC_A>, dim3(std::min(tiles, num_sms)), dim3(IG_THREADS), smem, st, p);
 }
 
 }  // namespace

@@ -127,6 +127,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                 // everything above touched only shared memory, TMEM and weights
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -448,8 +450,7 @@ cudaError_t launch_conv_tma(const TmaPlan& plan, const float* bias, void* out, c
       if (e != cudaSuccess) return e;                                                                               \
       attr = smem;                                                                                                  \
     }                                                                                                               \
-    kern<<<grid, TM_THREADS, smem, st>>>(*tm, p);                                                                   \
-    lerr = cudaGetLastError();                                                                                      \
+    lerr = launch_pdl(kern, dim3(grid), dim3(TM_THREADS), smem, st, *tm, p);                                        \
   }
   UAHN_TMA_CASE(7, 1, 1, 2, 0)   // block_4_0 / block_3_0 : 7x7 s1, Cin 2
   UAHN_TMA_CASE(5, 2, 2, 4, 2)   // block_4_1            : 5x5 s2, Cin 8  (run 88)

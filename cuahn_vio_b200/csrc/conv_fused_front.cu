@@ -168,6 +168,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  pdl_wait();                 // everything above touched only shared memory, TMEM and weights
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -547,13 +549,15 @@ cudaError_t launch_conv_fused(const FusedPlan& plan, void* out, const ConvGeom& 
     cfg.blockDim = dim3(FF_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = use_pair ? 2 : 1;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kern, *tm, p);
   };
   cudaError_t lerr;

@@ -18,6 +18,18 @@
 
 using namespace uahn;
 
+namespace uahn {
+// Programmatic dependent launch pays on the latency path (batch 1: 27 dependent kernels of a few microseconds each,
+// -9 % p50) and costs throughput on large batches (early-launched CTAs of the next kernel sit on the SMs of a
+// persistent kernel that still runs: -8 % at 1024 pairs), so forward() switches it per call.
+static thread_local bool g_pdl_on = false;
+bool pdl_enabled() {
+  static const bool allowed = getenv("UAHN_NO_PDL") == nullptr;
+  return allowed && g_pdl_on;
+}
+void pdl_select(int n_pairs) { g_pdl_on = n_pairs <= 8; }
+}  // namespace uahn
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -433,6 +445,7 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
   const int variant = h->cfg.variant;
   const float* Hcur = nullptr;
   int rc;
+  pdl_select(n);
   if (variant != UAHN_VARIANT_FULL) {
     if (!prior) return h->fail(UAHN_ERR_INVALID, "this variant needs a prior");
     h->prof_begin(3);

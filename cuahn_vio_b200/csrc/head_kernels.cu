@@ -76,6 +76,8 @@ __device__ __forceinline__ void mat3_mul(const float* A, const float* B, float* 
 
 // H = DLT(pts0, pts0 + off); optional left-multiplication by Hprev.  One warp per pair.
 __global__ void dlt_kernel(int n, const float* __restrict__ off, const float* __restrict__ Hprev, float* __restrict__ Hout) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (pair >= n) return;
   float dst[8];
@@ -114,6 +116,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) fc8_dlt_kernel(int n, const T* __restrict__ feat, const float* __restrict__ W8,
                                                        const float* __restrict__ b8, const float* __restrict__ Hprev,
                                                        float* __restrict__ Hout, float* __restrict__ dout) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float part[8][FC8_PAIRS][8];
   __shared__ float d_s[FC8_PAIRS][8];
   const int pair0 = blockIdx.x * FC8_PAIRS, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -190,6 +194,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) mc_expand_kernel(const T* __restrict__ feat, T* __restrict__ A, int n,
                                                          const uint8_t* __restrict__ keep_masks, uint64_t seed,
                                                          uint64_t first_pair, const uint64_t* __restrict__ rng_dev) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }   // graph replay: values live in device memory
   const int pair = blockIdx.x, head = blockIdx.y;
   const T* f = feat + (size_t)pair * FC_IN;
@@ -234,6 +240,8 @@ __global__ void __launch_bounds__(256) mc_expand_kernel(const T* __restrict__ fe
 __global__ void __launch_bounds__(256) mc_maskbits_kernel(uint8_t* __restrict__ bits_out, int n,
                                                            const uint8_t* __restrict__ keep_masks, uint64_t seed,
                                                            uint64_t first_pair, const uint64_t* __restrict__ rng_dev) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }
   const int pair = blockIdx.x, head = blockIdx.y;
   uint8_t* o = bits_out + ((size_t)head * n + pair) * (FC_IN / 8) * MC;
@@ -272,6 +280,8 @@ __global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid
                                                         const uint8_t* __restrict__ keep_masks, uint64_t seed,
                                                         uint64_t first_pair, const uint64_t* __restrict__ rng_dev,
                                                         HeadOut o) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }
   __shared__ __align__(16) float w2[2][8][FC_HID + 4];   // +4 floats: the 8 output rows hit 8 different bank groups
   __shared__ float outv[2][MC][8];
@@ -407,15 +417,13 @@ __global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid
 
 cudaError_t launch_dlt(int n, const float* off, const float* Hprev, float* Hout, cudaStream_t st) {
   const int threads = 128, pairs_per_block = threads / 32;
-  dlt_kernel<<<(n + pairs_per_block - 1) / pairs_per_block, threads, 0, st>>>(n, off, Hprev, Hout);
-  return cudaGetLastError();
+  return launch_pdl(dlt_kernel, dim3((n + pairs_per_block - 1) / pairs_per_block), dim3(threads), 0, st, n, off, Hprev, Hout);
 }
 
 template <typename T>
 cudaError_t launch_fc8_dlt(int n, const T* feat, const float* W8, const float* b8, const float* Hprev, float* Hout,
                            float* dout, cudaStream_t st) {
-  fc8_dlt_kernel<T><<<(n + FC8_PAIRS - 1) / FC8_PAIRS, 256, 0, st>>>(n, feat, W8, b8, Hprev, Hout, dout);
-  return cudaGetLastError();
+  return launch_pdl(fc8_dlt_kernel<T>, dim3((n + FC8_PAIRS - 1) / FC8_PAIRS), dim3(256), 0, st, n, feat, W8, b8, Hprev, Hout, dout);
 }
 template cudaError_t launch_fc8_dlt<float>(int, const float*, const float*, const float*, const float*, float*, float*,
                                            cudaStream_t);
@@ -425,8 +433,7 @@ template cudaError_t launch_fc8_dlt<__nv_bfloat16>(int, const __nv_bfloat16*, co
 template <typename T>
 cudaError_t launch_mc_expand(int n, const T* feat, T* A, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,
                              const uint64_t* rng_dev, cudaStream_t st) {
-  mc_expand_kernel<T><<<dim3(n, 2), 256, 0, st>>>(feat, A, n, keep_masks, seed, first_pair, rng_dev);
-  return cudaGetLastError();
+  return launch_pdl(mc_expand_kernel<T>, dim3(n, 2), dim3(256), 0, st, feat, A, n, keep_masks, seed, first_pair, rng_dev);
 }
 template cudaError_t launch_mc_expand<float>(int, const float*, float*, const uint8_t*, uint64_t, uint64_t,
                                              const uint64_t*, cudaStream_t);
@@ -435,8 +442,7 @@ template cudaError_t launch_mc_expand<__nv_bfloat16>(int, const __nv_bfloat16*, 
 
 cudaError_t launch_mc_maskbits(int n, uint8_t* bits, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,
                                const uint64_t* rng_dev, cudaStream_t st) {
-  mc_maskbits_kernel<<<dim3(n, 2), 256, 0, st>>>(bits, n, keep_masks, seed, first_pair, rng_dev);
-  return cudaGetLastError();
+  return launch_pdl(mc_maskbits_kernel, dim3(n, 2), dim3(256), 0, st, bits, n, keep_masks, seed, first_pair, rng_dev);
 }
 
 template <typename T>
@@ -445,8 +451,7 @@ cudaError_t launch_mc_final(int n, const T* hid, const float* W2m, const float* 
                             uint64_t first_pair, const uint64_t* rng_dev, float* mean, float* cov, float* Htot,
                             float* mc_mean, float* mc_logvar, cudaStream_t st) {
   HeadOut o{mean, cov, Htot, mc_mean, mc_logvar};
-  mc_final_kernel<T><<<n, 256, 0, st>>>(hid, n, W2m, b2m, W2u, b2u, Hpart1, keep_masks, seed, first_pair, rng_dev, o);
-  return cudaGetLastError();
+  return launch_pdl(mc_final_kernel<T>, dim3(n), dim3(256), 0, st, hid, n, W2m, b2m, W2u, b2u, Hpart1, keep_masks, seed, first_pair, rng_dev, o);
 }
 template cudaError_t launch_mc_final<float>(int, const float*, const float*, const float*, const float*, const float*,
                                             const float*, const uint8_t*, uint64_t, uint64_t, const uint64_t*, float*,
