@@ -78,6 +78,7 @@ const LayerSpec B1[] = {{"block_1_1", 128, 2, 7, 2}, {"block_1_2", 128, 128, 5, 
 const LayerSpec B2[] = {{"block_2_1", 64, 2, 7, 2}, {"block_2_2", 128, 64, 5, 2}, {"block_2_3", 256, 128, 3, 2}, {"block_2_4", 256, 256, 3, 2}};
 const LayerSpec B3[] = {{"block_3_0", 16, 2, 7, 1}, {"block_3_1", 32, 16, 5, 2}, {"block_3_2", 64, 32, 3, 2}, {"block_3_3", 128, 64, 3, 2}, {"block_3_4", 256, 128, 3, 2}, {"block_3_5", 256, 256, 3, 2}};
 const LayerSpec B4[] = {{"block_4_0", 8, 2, 7, 1}, {"block_4_1", 16, 8, 5, 2}, {"block_4_2", 32, 16, 3, 2}, {"block_4_3", 64, 32, 3, 2}, {"block_4_4", 128, 64, 3, 2}, {"block_4_5", 256, 128, 3, 2}, {"block_4_6", 256, 256, 3, 2}};
+constexpr int MC_SMALL_MAX_PAIRS = 8;    // bf16: up to here the first MC-head layer runs on CUDA cores (latency path)
 constexpr int MC_FUSED_MIN_PAIRS = 64;   // bf16: batches from this size on use the fused masked-A MC GEMM
 const char* P1 = "model_part1.";
 const char* P4 = "model_last_block_list.0.";
@@ -119,6 +120,7 @@ struct uahn_handle {
   // block-4 head
   float *W1m = nullptr, *b1m = nullptr, *W1u = nullptr, *b1u = nullptr;       // [5120][256] fp32 (k' order)
   ConvBf16Weights W1m_b, W1u_b;
+  void *W1m_plain = nullptr, *W1u_plain = nullptr;   // [256][5120] bf16, NHWC k order: the batch-1 CUDA-core first layer
   float *W2m = nullptr, *b2m = nullptr, *W2u = nullptr, *b2u = nullptr;
   void* mcA = nullptr;    // [2][n][16][5120] masked features (fp32, small bf16 batches) or keep bits [2][n][640][16] bytes
   void* hid = nullptr;    // [2][cap][16][256] T
@@ -357,9 +359,9 @@ int build_block(uahn_handle* h, const std::map<std::string, HostTensor>& w, int 
 int build_head(uahn_handle* h, const std::map<std::string, HostTensor>& w) {
   std::string err;
   int rc;
-  struct { const char* name; float** W1; float** b1; float** W2; float** b2; ConvBf16Weights* wb; } heads[2] = {
-      {"fc_block_4_mean", &h->W1m, &h->b1m, &h->W2m, &h->b2m, &h->W1m_b},
-      {"fc_block_4_uncertainty", &h->W1u, &h->b1u, &h->W2u, &h->b2u, &h->W1u_b}};
+  struct { const char* name; float** W1; float** b1; float** W2; float** b2; ConvBf16Weights* wb; void** plain; } heads[2] = {
+      {"fc_block_4_mean", &h->W1m, &h->b1m, &h->W2m, &h->b2m, &h->W1m_b, &h->W1m_plain},
+      {"fc_block_4_uncertainty", &h->W1u, &h->b1u, &h->W2u, &h->b2u, &h->W1u_b, &h->W1u_plain}};
   for (auto& hd : heads) {
     const std::string key = std::string(P4) + hd.name;
     const HostTensor* w1 = find(w, key + ".1.weight", {FC_HID, FC_IN}, err);
@@ -375,6 +377,12 @@ int build_head(uahn_handle* h, const std::map<std::string, HostTensor>& w) {
       Tensor tin{}, tout{};
       if (conv_bf16_prepare(*hd.wb, wk, b1->data, dense_geom(1, FC_IN, FC_HID, 1), tin, tout, h->allocs, err))
         return h->fail(UAHN_ERR_UNSUPPORTED, "%s: %s", hd.name, err.c_str());
+      std::vector<uint16_t> plain(perm.size());
+      for (size_t i = 0; i < perm.size(); ++i) plain[i] = f32_to_bf16_host(perm[i]);
+      uint16_t* dp = nullptr;
+      if ((rc = dev_alloc(h, &dp, plain.size(), false))) return rc;
+      CK(cudaMemcpy(dp, plain.data(), plain.size() * 2, cudaMemcpyHostToDevice));
+      *hd.plain = dp;
     } else {
       if ((rc = upload(h, hd.W1, wk))) return rc;
     }
@@ -484,6 +492,8 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
       T* o = (T*)h->hid + (size_t)head * n * MC * FC_HID;
       if constexpr (sizeof(T) == 4) {
         LAUNCH(launch_conv_f32((const float*)a, head ? h->W1u : h->W1m, head ? h->b1u : h->b1m, (float*)o, g, st));
+      } else if (n <= MC_SMALL_MAX_PAIRS) {     // latency path: CUDA-core kernel, 64 CTAs per pair and head
+        LAUNCH(launch_mc_fc1_small(n, a, head ? h->W1u_plain : h->W1m_plain, head ? h->b1u : h->b1m, o, st));
       } else {
         LAUNCH(launch_conv_bf16(head ? h->W1u_b : h->W1m_b, a, head ? h->b1u : h->b1m, o, g, st));
       }

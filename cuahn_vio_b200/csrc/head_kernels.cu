@@ -7,6 +7,7 @@
 //     (model_to_trace.py:18-38), output packing and the showError homography (model_to_trace.py:311-323)
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_ptx.cuh"
 
 namespace uahn {
 namespace {
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(256) fc8_dlt_kernel(int n, const T* __restrict
   for (int p = 0; p < FC8_PAIRS; ++p)
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[p][o] = 0.f;
+#pragma unroll 5        // 20 trips; 5 x (8 weight + np feature) loads in flight per thread: the loop is L2-latency-bound
   for (int k = tid; k < FC_IN; k += 256) {
     float w[8], x[FC8_PAIRS];
 #pragma unroll
@@ -231,6 +233,64 @@ __global__ void __launch_bounds__(256) mc_expand_kernel(const T* __restrict__ fe
       *reinterpret_cast<float4*>(dstp) = *reinterpret_cast<const float4*>(v);
       *reinterpret_cast<float4*>(dstp + 4) = *reinterpret_cast<const float4*>(v + 4);
     }
+  }
+}
+
+// First MC-head layer for the batch-1 latency path: hid[pair][s][j] = LeakyReLU(sum_k A[pair][s][k] * W[j][k] + b[j]) on
+// CUDA cores.  With one or a few pairs the tensor-core GEMM is a handful of CTAs each walking all 80 K stages in
+// sequence (25 us per head at batch 1); here 64 CTAs per pair and head each take 4 output columns, read the 16 masked
+// sample rows once, and reduce across the block.  A: [n][16][5120] bf16 (mc_expand), W: [256][5120] bf16 in the same
+// (NHWC) k order, out: [n][16][256] bf16 with the tensor path's epilogue arithmetic (bf16 round, LeakyReLU on bf16).
+constexpr int FC1S_JT = 4;
+__global__ void __launch_bounds__(256) mc_fc1_small_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
+                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float part[8][MC][FC1S_JT];
+  const int j0 = blockIdx.x * FC1S_JT, pair = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint4* a4 = reinterpret_cast<const uint4*>(A + (size_t)pair * MC * FC_IN);
+  const uint4* w4 = reinterpret_cast<const uint4*>(W + (size_t)j0 * FC_IN);
+  float acc[MC][FC1S_JT];
+#pragma unroll
+  for (int s = 0; s < MC; ++s)
+#pragma unroll
+    for (int j = 0; j < FC1S_JT; ++j) acc[s][j] = 0.f;
+  auto lo = [](uint32_t v) { return __uint_as_float(v << 16); };
+  auto hi = [](uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); };
+  for (int g = tid; g < FC_IN / 8; g += 256) {
+    float wf[FC1S_JT][8];
+#pragma unroll
+    for (int j = 0; j < FC1S_JT; ++j) {
+      const uint4 w = __ldg(w4 + (size_t)j * (FC_IN / 8) + g);
+      wf[j][0] = lo(w.x); wf[j][1] = hi(w.x); wf[j][2] = lo(w.y); wf[j][3] = hi(w.y);
+      wf[j][4] = lo(w.z); wf[j][5] = hi(w.z); wf[j][6] = lo(w.w); wf[j][7] = hi(w.w);
+    }
+#pragma unroll
+    for (int s = 0; s < MC; ++s) {
+      const uint4 a = __ldg(a4 + (size_t)s * (FC_IN / 8) + g);
+      const float af[8] = {lo(a.x), hi(a.x), lo(a.y), hi(a.y), lo(a.z), hi(a.z), lo(a.w), hi(a.w)};
+#pragma unroll
+      for (int j = 0; j < FC1S_JT; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[s][j] = fmaf(af[e], wf[j][e], acc[s][j]);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < MC; ++s)
+#pragma unroll
+    for (int j = 0; j < FC1S_JT; ++j) {
+      float v = acc[s][j];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) part[wid][s][j] = v;
+    }
+  __syncthreads();
+  if (tid < MC * FC1S_JT / 2) {            // one thread per pair of adjacent output columns
+    const int s = tid / (FC1S_JT / 2), jp = (tid % (FC1S_JT / 2)) * 2;
+    float v0 = bias[j0 + jp], v1 = bias[j0 + jp + 1];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { v0 += part[w][s][jp]; v1 += part[w][s][jp + 1]; }
+    reinterpret_cast<uint32_t*>(out + ((size_t)pair * MC + s) * FC_HID + j0 + jp)[0] = pack_lrelu_bf16x2(v0, v1);
   }
 }
 
@@ -439,6 +499,11 @@ template cudaError_t launch_mc_expand<float>(int, const float*, float*, const ui
                                              const uint64_t*, cudaStream_t);
 template cudaError_t launch_mc_expand<__nv_bfloat16>(int, const __nv_bfloat16*, __nv_bfloat16*, const uint8_t*,
                                                      uint64_t, uint64_t, const uint64_t*, cudaStream_t);
+
+cudaError_t launch_mc_fc1_small(int n, const void* A, const void* W, const float* bias, void* out, cudaStream_t st) {
+  return launch_pdl(mc_fc1_small_kernel, dim3(FC_HID / FC1S_JT, n), dim3(256), 0, st, (const __nv_bfloat16*)A,
+                    (const __nv_bfloat16*)W, bias, (__nv_bfloat16*)out);
+}
 
 cudaError_t launch_mc_maskbits(int n, uint8_t* bits, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,
                                const uint64_t* rng_dev, cudaStream_t st) {
