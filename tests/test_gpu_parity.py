@@ -363,6 +363,31 @@ def test_fused_front_matches_per_layer_kernels(api, wfile):
     assert np.abs(outs[True][0] - outs[False][0]).max() < BF16_PX
 
 
+def test_edge_inputs_fp32_vs_oracle(api, wfile, synth_sd):
+    """Degenerate frames and a prior that throws the warp (mostly) outside the image: black, saturated, identical
+    frames, a 250-px shift; n == max_batch and n < max_batch through the same handle."""
+    prev, curr, _, prior = S.synthetic_batch(2, start=950)
+    z = np.zeros((224, 320), np.uint8)
+    frames_p = np.stack([z, z + 255, prev[0], prev[1], prev[1]])
+    frames_c = np.stack([z, z + 255, prev[0], curr[1], curr[1]])
+    pri = np.zeros((5, 4, 2), np.float32)
+    pri[3] = prior[1] + np.float32(250.0)          # warp window almost entirely outside the frame
+    pri[4] = prior[1]
+    masks = _masks_for(5)
+    om, oc, oe = _oracle_batch(frames_p, frames_c, synth_sd, masks, pri, True)
+    assert np.isfinite(om).all() and np.isfinite(oc).all()
+    with api.Uahn(wfile, "prior3", show_error=True, precision="fp32", max_batch=5) as net:
+        m, c, e = net.infer_batch(frames_p, frames_c, pri, keep_masks=_pack(api, masks), want_error=True)   # n == max_batch
+        assert np.isfinite(m).all() and np.isfinite(c).all()
+        assert np.abs(m - om).max() < FP32_PX, np.abs(m - om).max()
+        assert np.abs(c - oc).max() <= 5e-4 * np.abs(oc).max()
+        assert np.abs(e - oe).max() < 0.05          # grey levels of 255: the <= 1e-4 px difference of H_total times the image gradient
+        m1, c1, _ = net.infer_batch(frames_p[3:4], frames_c[3:4], pri[3:4], keep_masks=_pack(api, masks[3:4]))   # n < max_batch
+        assert np.array_equal(m1[0], m[3]) and np.array_equal(c1[0], c[3])
+        with pytest.raises(api.UahnError):
+            net.infer_batch(frames_p[:0], frames_c[:0], pri[:0])                                            # empty batch
+
+
 @pytest.mark.parametrize("variant", ["prior3", "full"])
 def test_e2e_bf16_vs_oracle(api, wfile, synth_sd, variant):
     n = 5
