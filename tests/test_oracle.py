@@ -8,8 +8,11 @@ from oracle import uahn_oracle as O
 
 
 def _tol(g):
-    # bit-exact when the torch build matches the one that made the fixtures; otherwise fp32 noise
-    return 0.0 if str(g["torch_version"]) == torch.__version__ else 2e-4
+    # bit-exact in the container that made the fixtures (same torch build, same CPU kernels: /root/reference is only
+    # mounted there); on other hosts oneDNN / MKL pick other code paths for the same ops, so: fp32 noise
+    import os
+    same_host = str(g["torch_version"]) == torch.__version__ and os.path.isdir("/root/reference")
+    return 0.0 if same_host else 2e-4
 
 
 def test_masks_replay_matches_torch_seed(golden_e2e):
