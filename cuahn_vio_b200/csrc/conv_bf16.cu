@@ -12,8 +12,9 @@
 //   Cout = 8/16/32 layers fill a 128 x N tensor-core tile: N = XB*Cout.
 // * B (weights) is prepared once on the host as the exact shared-memory image of every K stage, so a stage
 //   is one cp.async.bulk (TMA bulk copy, UBLKCP) completing on the stage's mbarrier.
-// * Warp roles: warps 0-3 gather A then run the epilogue (tcgen05.ld -> bias + LeakyReLU -> bf16 -> global),
-//   warp 4 issues tcgen05.mma from one elected lane, warp 5 streams B.  Full/empty mbarriers per stage;
+// * Warp roles: warps 0-3 gather A (or, MC_A, build the MC-dropout expansion of the block-4 feature on the fly),
+//   warp 4 issues tcgen05.mma from one elected lane, warp 5 streams B, warps 6-9 run the epilogue (tcgen05.ld ->
+//   bias -> bf16 -> LeakyReLU -> 64-column staging -> coalesced global).  Full/empty mbarriers per stage;
 //   tcgen05.commit releases a stage when the MMAs that read it retire.
 #include <algorithm>
 #include <cmath>

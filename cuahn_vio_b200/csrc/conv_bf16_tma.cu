@@ -17,9 +17,10 @@
 // x-direction taps and the conv stride in x live in the banded ("Toeplitz") B operand, which is small enough
 // to stay resident in shared memory for the lifetime of the persistent CTA.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-5 = epilogue (TMEM -> bias + LeakyReLU ->
-// bf16 -> smem -> coalesced global).  Planes flow through a ring of n_slots shared-memory slots guarded by
-// full/empty mbarriers; two TMEM accumulators overlap the epilogue of tile i with the MMAs of tile i+1.
+// Warp roles: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-17 = epilogue (TMEM -> bf16 -> LeakyReLU on
+// the packed pair -> each thread stores its 32 contiguous output bytes; the accumulators are pre-loaded with the bias
+// and re-armed by every drain).  Planes flow through a ring of n_slots shared-memory slots guarded by full/empty
+// mbarriers; two TMEM accumulators overlap the epilogue of tile i with the MMAs of tile i+1.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>

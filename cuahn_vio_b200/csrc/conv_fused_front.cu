@@ -6,17 +6,22 @@
 //
 // Tile = 7 x 14 patch of conv-2 pixel groups (one group = 64/C2 output pixels = G1 = 64/C1 conv-1 pixels = one
 // 128-byte K row).  Per tile:
-//   1. TMA: one 4-D box {64 el, 8 groups, 38 rows} of the 2-channel block input (overlapping x windows, halo 5).
+//   1. TMA: one 4-D box {64 el, 8 groups, 38 rows} of the 2-channel block input (overlapping x windows, halo 5),
+//      double-buffered and fetched a tile ahead.
 //   2. conv 1 as two 128-row MMA tiles (rows 0-15 / 16-31 of the 32 x 8-group region conv 2 needs); kernel row ky is
 //      the same plane shifted by ky rows (shifted-window trick of conv_bf16_tma.cu); weights packed two taps per
-//      64-element B stage.
-//   3. 16 epilogue warps: D1 -> +bias, LeakyReLU, zero outside the image (that is conv 2's zero padding) -> bf16 ->
-//      shared-memory planes [row parity][t = row/2][group], 128B-swizzled by ADDRESS (the UMMA swizzle is purely
-//      address-based — tools/umma_offset_test.cu — so operands may start at any 128-byte row).
+//      64-element B stage.  The accumulators were pre-loaded with the bias (tcgen05.st), every MMA accumulates.
+//   3. conv-1 epilogue warps (2..9): D1 -> bf16 -> LeakyReLU on the packed pair, zero outside the image (conv 2's zero
+//      padding) -> shared-memory planes [row parity][t = row/2][group], 128B-swizzled by ADDRESS (the UMMA swizzle is
+//      purely address-based — tools/umma_offset_test.cu — so operands may start at any 128-byte row); then they re-arm
+//      D1 with the bias.
 //   4. conv 2: tap ky = rho + 2a, chunk c reads plane rho at row offset (a*8 + c): "chunk 1 of group w" is "chunk 0
-//      of group w+1", so nothing is duplicated.  B2 (80 KB) and B1 (32 KB) stay resident in shared memory.
-//   5. epilogue: D2 -> +bias, LeakyReLU -> bf16 -> staged, coalesced stores into the (haloed NHWC) conv-2 output.
-// conv 1 of tile i+1 overlaps the conv-2 epilogue of tile i (separate TMEM accumulators, mbarrier hand-offs).
+//      of group w+1", so nothing is duplicated.  B2 and B1 stay resident in shared memory.
+//   5. conv-2 epilogue warps (10..17): D2 -> bf16 -> LeakyReLU -> each thread stores its 64 contiguous bytes of the
+//      (haloed NHWC) conv-2 output.
+// The MMA warp issues conv 1 of tile k+1 AHEAD of conv 2 of tile k (D1 double-buffered in TMEM), so the tensor pipe
+// works through the D1 -> planes hand-off instead of idling on it.  PAIR: clusters of two CTAs share every UMMA
+// (tcgen05.mma.cta_group::2, M = 256), each holding half of B; the freed shared memory double-buffers the planes.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
