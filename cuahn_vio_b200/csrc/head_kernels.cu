@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(256) mc_maskbits_kernel(uint8_t* __restrict__ 
   if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }
   const int pair = blockIdx.x, head = blockIdx.y;
   uint8_t* o = bits_out + ((size_t)head * n + pair) * (FC_IN / 8) * MC;
+#pragma unroll 4      // independent Philox chains per thread: the kernel is the latency of 7 dependent multiply rounds
   for (int i = threadIdx.x; i < MC * (FC_IN / 8); i += blockDim.x) {
     const int k8 = i / MC, smp = i - k8 * MC;            // consecutive threads -> consecutive bytes
     uint32_t bits;
