@@ -19,7 +19,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
+
+#include <cudaTypedefs.h>
 
 #include "conv_bf16.h"
 #include "tc_ptx.cuh"
@@ -49,7 +52,10 @@ struct IgemmParams {
   int n_total, n_tiles, m_tiles;
   int act;
   const uint8_t* mc_bits;   // MC_A mode: keep bits [pair][k8][16 samples] of this head (head_kernels.cu)
+  // AM_IM2COL mode
+  int Ho, stride, KW, cin_chunks;
 };
+constexpr int AM_GATHER = 0, AM_MC = 1, AM_IM2COL = 2;
 
 template <int BN>
 constexpr int tmem_cols() { return 2 * BN < 32 ? 32 : 2 * BN; }   // two accumulator buffers
@@ -67,8 +73,13 @@ constexpr int stage_row_bytes() { return epi_chunk<BN>() * 2 + 16; }   // stagin
 // 272-273): GEMM row (pair, sample) = keep-mask(pair, sample) * feature(pair) / 0.95.  The producer reads each 16-byte
 // feature granule once per pair, scales it, and writes 16 masked copies straight into the swizzled stage; the masked
 // features (327 KB per pair and head) never exist in HBM.
-template <int BN, int STAGES, bool B_RES, bool MC_A = false>
-__global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __grid_constant__ IgemmParams p) {
+// AM_IM2COL: the A stage of (filter tap, 64-channel chunk) is ONE im2col-mode TMA load of 128 consecutive output
+// positions x 64 channels, written by the TMA unit straight into the 128B-swizzled stage (layers with Cin % 64 == 0:
+// a K stage is exactly one tap and channel chunk).  One elected thread issues it together with the stage's B copy.
+template <int BN, int STAGES, bool B_RES, int AM = AM_GATHER>
+__global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __grid_constant__ IgemmParams p,
+                                                                         const __grid_constant__ CUtensorMap amap) {
+  constexpr bool MC_A = AM == AM_MC;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * 128;
   constexpr int SROW = stage_row_bytes<BN>();
@@ -92,7 +103,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
-        mbar_init(full0 + 8 * s, B_RES ? 128 : 129);   // 128 producer threads (+ the B loader's expect_tx arrive)
+        // 128 producer threads (+ the B loader's expect_tx arrive); im2col: one arrive.expect_tx for A and B together
+        mbar_init(full0 + 8 * s, AM == AM_IM2COL ? 1 : (B_RES ? 128 : 129));
         mbar_init(empty0 + 8 * s, 1);                  // one tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
@@ -116,7 +128,30 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   pdl_wait();                 // everything above touched only shared memory, TMEM and weights
   pdl_launch_dependents();    // persistent grid: all CTAs are resident, the next kernel may start its prologue
 
-  if (MC_A && warp < 4) {
+  if (AM == AM_IM2COL && warp < 4) {
+    // ===================== im2col TMA producer: one thread issues A (TMA im2col) and B (bulk copy) per stage ==========
+    if (warp == 0 && lane == 0) {
+      tma_prefetch_desc(&amap);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+        const int img = fast_div(m0, p.magic_rows), rem = m0 - img * p.rows_per_img;
+        const int oy = fast_div(rem, p.magic_wox), ox = rem - oy * p.Wox;
+        int tap = 0, ky = 0, kx = 0, cc = 0;
+        for (int s = 0; s < p.k_stages; ++s, ++it) {
+          const int slot = it % STAGES;
+          mbar_wait(empty0 + 8 * slot, ((it / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(full0 + 8 * slot, (uint32_t)(A_STAGE_BYTES + (B_RES ? 0 : B_STAGE_BYTES)));
+          tma_load_im2col_4d(smem_u32(sA + slot * A_STAGE_BYTES), &amap, cc * 64, ox * p.stride, oy * p.stride, img,
+                             (uint16_t)kx, (uint16_t)ky, full0 + 8 * slot);
+          if (!B_RES)
+            bulk_g2s(smem_u32(sB + slot * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES,
+                     full0 + 8 * slot);
+          if (++cc == p.cin_chunks) { cc = 0; ++tap; if (++kx == p.KW) { kx = 0; ++ky; } }
+        }
+      }
+    }
+  } else if (MC_A && warp < 4) {
     // ===================== masked-feature producer (MC-dropout GEMM) =====================
     // thread -> (pair of the tile, granule j of the stage, 8 of the 16 samples); tile = 8 pairs x 16 samples
     const int pl = tid >> 4, j = tid & 7, hs = (tid >> 3) & 1;
@@ -271,7 +306,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
         mbar_arrive_expect_tx(bres, (uint32_t)(p.k_stages * B_STAGE_BYTES));
         for (int s = 0; s < p.k_stages; ++s)
           bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES, bres);
-      } else {
+      } else if (AM != AM_IM2COL) {
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
           const int n0 = (tile % p.n_tiles) * BN;
@@ -359,19 +394,21 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
 template <int BN>
 constexpr size_t fixed_smem() { return 1024 + 128 * (size_t)stage_row_bytes<BN>() + 256 * 4 + 128 * 8 + 64 * 8; }
 
-template <int BN, int STAGES, bool B_RES, bool MC_A = false>
-cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st) {
+template <int BN, int STAGES, bool B_RES, int AM = AM_GATHER>
+cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st, const CUtensorMap* amap = nullptr) {
   const size_t smem = fixed_smem<BN>() + (size_t)STAGES * A_STAGE_BYTES + (size_t)(B_RES ? p.k_stages : STAGES) * BN * 128;
   if (smem > SMEM_LIMIT) return cudaErrorInvalidConfiguration;
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_bf16_kernel<BN, STAGES, B_RES, MC_A>,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_bf16_kernel<BN, STAGES, B_RES, AM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = smem;
   }
   const int tiles = p.m_tiles * p.n_tiles;
-  return launch_pdl(conv_igemm_bf16_kernel<BN, STAGES, B_RES, MC_A>, dim3(std::min(tiles, num_sms)), dim3(IG_THREADS), smem, st, p);
+  static const CUtensorMap no_map{};
+  return launch_pdl(conv_igemm_bf16_kernel<BN, STAGES, B_RES, AM>, dim3(std::min(tiles, num_sms)), dim3(IG_THREADS), smem, st, p,
+                    amap ? *amap : no_map);
 }
 
 }  // namespace
@@ -417,7 +454,9 @@ int conv_bf16_prepare(ConvBf16Weights& wb, const std::vector<float>& wk, const s
     if (rc < 0) { err = terr; return rc; }
     if (wb.tma.enabled) { wb.ready = 1; return 0; }
   }
-  const int xb = choose_xb(g);
+  // im2col TMA A producer: layers whose K stage is exactly one (tap, 64-channel chunk)
+  const bool im2col_ok = in.p && g.Cin % 64 == 0 && g.KH == g.KW && g.KH > 1 && !getenv("UAHN_NO_IM2COL");
+  const int xb = im2col_ok ? 1 : choose_xb(g);
   if (!xb) { err = "no valid Toeplitz factor"; return -1; }
   if (g.Cin % 8 && !(g.Cin == 2 && (xb * g.stride) % 4 == 0)) { err = "unsupported Cin"; return -1; }
   const int n_total = xb * g.Cout;
@@ -454,6 +493,34 @@ int conv_bf16_prepare(ConvBf16Weights& wb, const std::vector<float>& wk, const s
   if (cudaMalloc(&db, bx.size() * 4) != cudaSuccess) { err = "cudaMalloc(bias)"; return -2; }
   allocs.push_back(db);
   if (cudaMemcpy(db, bx.data(), bx.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { err = "memcpy(bias)"; return -2; }
+  if (im2col_ok) {
+    static PFN_cuTensorMapEncodeIm2col_v12000 encode = nullptr;
+    if (!encode) {
+      void* fp = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fp, cudaEnableDefault, &qres) == cudaSuccess &&
+          qres == cudaDriverEntryPointSuccess)
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fp);
+    }
+    if (encode) {
+      const int p_ = (g.KH - 1) / 2, s_ = g.stride;
+      const int Wt = in.Wp - (in.pwl - p_), Ht = in.Hp - (in.ph - p_);     // extents seen from the window origin
+      const cuuint64_t gdim[4] = {(cuuint64_t)g.Cin, (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)in.N};
+      const cuuint64_t gstr[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.in_pitch_y * 2, (cuuint64_t)g.in_pitch_n * 2};
+      // base pixels (window origins) run over [0, W + upper): exactly Wo x Ho positions per image at the conv stride
+      const int lower[2] = {0, 0};
+      const int upper[2] = {s_ * (g.Wo - 1) + 1 - Wt, s_ * (g.Ho - 1) + 1 - Ht};
+      const cuuint32_t estr[4] = {1, (cuuint32_t)s_, (cuuint32_t)s_, 1};
+      void* base = (uint8_t*)in.p + g.in_origin * 2;
+      const CUresult r = encode(reinterpret_cast<CUtensorMap*>(wb.im2col_map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim,
+                                gstr, lower, upper, 64, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      wb.im2col = r == CUDA_SUCCESS;
+      if (getenv("UAHN_DEBUG"))
+        fprintf(stderr, "[uahn] im2col TMA map Cin=%d k=%d s=%d out=%dx%d: W'=%d H'=%d upper=(%d,%d) -> %s\n", g.Cin, g.KH, s_,
+                g.Ho, g.Wo, Wt, Ht, upper[0], upper[1], wb.im2col ? "ok" : "encode failed, cp.async gather");
+    }
+  }
   wb.b_image = d;
   wb.bias_x = (float*)db;
   wb.xb = xb;
@@ -492,7 +559,7 @@ cudaError_t launch_mc_gemm_bf16(const ConvBf16Weights& wb, const void* feat, con
   p.act = 1;
   p.m_tiles = (p.M_rows + BM - 1) / BM;
   p.n_tiles = 1;
-  return launch_t<256, 4, false, true>(p, num_sms, st);
+  return launch_t<256, 4, false, AM_MC>(p, num_sms, st);
 }
 
 cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const float* bias, void* out,
@@ -541,6 +608,16 @@ cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const fl
   p.n_tiles = p.n_total / bn;
   // B resident in shared memory when the whole operand of this N tile fits next to a 4-stage A ring
   const bool res = p.n_tiles == 1 && (size_t)p.k_stages * bn * 128 <= 112 * 1024;
+  if (wb.im2col) {
+    p.Ho = g.Ho; p.stride = g.stride; p.KW = g.KW; p.cin_chunks = g.Cin / 64;
+    const CUtensorMap* am = reinterpret_cast<const CUtensorMap*>(wb.im2col_map);
+    switch (bn) {
+      case 256: return launch_t<256, 4, false, AM_IM2COL>(p, num_sms, st, am);
+      case 128: return res ? launch_t<128, 5, true, AM_IM2COL>(p, num_sms, st, am) : launch_t<128, 6, false, AM_IM2COL>(p, num_sms, st, am);
+      case 64: return res ? launch_t<64, 5, true, AM_IM2COL>(p, num_sms, st, am) : launch_t<64, 8, false, AM_IM2COL>(p, num_sms, st, am);
+      default: break;   // narrower tiles: the gather path below
+    }
+  }
   switch (bn) {
     case 256: return launch_t<256, 4, false>(p, num_sms, st);
     case 128: return res ? launch_t<128, 5, true>(p, num_sms, st) : launch_t<128, 6, false>(p, num_sms, st);

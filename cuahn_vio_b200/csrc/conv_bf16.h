@@ -45,6 +45,9 @@ struct ConvBf16Weights {
   int k_total = 0;           // padded K (elements)
   int runs = 0, run_granules = 0;
   float* bias_x = nullptr;   // bias replicated xb times
+  // im2col TMA A producer (conv_bf16.cu, Cin % 64 == 0 layers): tensor map over the haloed NHWC input
+  int im2col = 0;
+  alignas(64) unsigned char im2col_map[128];
 };
 
 // wk: [K][Cout] fp32 with k = (ky*KW + kx)*Cin + c.  Appends device allocations to `allocs`.

@@ -233,6 +233,16 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar & PEER_BIT_MASK)
       : "memory");
 }
+// im2col-mode TMA (cp.async.bulk.tensor...im2col): pixelsPerColumn consecutive output positions starting at base pixel
+// (w, h) of image n — wrapping over rows and images inside the tensor map's bounding box, stepping by the conv stride —
+// times channelsPerPixel channels from c, for filter tap (off_w, off_h): one [pixels][channels] A tile of the implicit GEMM.
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* tmap, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6], {%7, %8};"
+      ::"r"(dst), "l"(tmap), "r"(c), "r"(w), "r"(h), "r"(n), "r"(bar), "h"(off_w), "h"(off_h)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
