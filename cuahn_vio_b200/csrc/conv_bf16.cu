@@ -54,8 +54,15 @@ struct IgemmParams {
   const uint8_t* mc_bits;   // MC_A mode: keep bits [pair][k8][16 samples] of this head (head_kernels.cu)
   // AM_IM2COL mode
   int Ho, stride, KW, cin_chunks;
+  unsigned long long* dbg;  // optional [grid][16] cycle counters (UAHN_IG_PROFILE)
 };
 constexpr int AM_GATHER = 0, AM_MC = 1, AM_IM2COL = 2;
+
+// -DUAHN_IG_PROFILE=1 + UAHN_IG_DEBUG=1: per-role cycle counters of the im2col-mode kernels (printed per launch)
+#ifndef UAHN_IG_PROFILE
+#define UAHN_IG_PROFILE 0
+#endif
+__device__ __forceinline__ long long ig_clock() { return UAHN_IG_PROFILE ? clock64() : 0ll; }
 
 template <int BN>
 constexpr int tmem_cols() { return 2 * BN < 32 ? 32 : 2 * BN; }   // two accumulator buffers
@@ -76,12 +83,21 @@ constexpr int stage_row_bytes() { return epi_chunk<BN>() * 2 + 16; }   // stagin
 // AM_IM2COL: the A stage of (filter tap, 64-channel chunk) is ONE im2col-mode TMA load of 128 consecutive output
 // positions x 64 channels, written by the TMA unit straight into the 128B-swizzled stage (layers with Cin % 64 == 0:
 // a K stage is exactly one tap and channel chunk).  One elected thread issues it together with the stage's B copy.
-template <int BN, int STAGES, bool B_RES, int AM = AM_GATHER>
+// PAIR: launched as clusters of two CTAs that share every UMMA (tcgen05.mma.cta_group::2, M = 256).  The two CTAs work
+// on consecutive M tiles of the same N tile; each keeps its own A ring, accumulators and epilogue but holds only HALF of
+// each B stage (BN/2 rows, loaded through a tiled tensor map over the pre-swizzled B image), so the B bytes an SM pulls
+// from L2 per tile halve — the deep layers are bound by exactly that ingest (64 B/clk per SM).  All loads of a stage
+// complete on the leader's full barrier; the leader's tcgen05.commit multicasts to the empty / accumulator-full
+// barriers of both CTAs; the peer's epilogue warps release the accumulator on the leader's barrier.
+template <int BN, int STAGES, bool B_RES, int AM = AM_GATHER, bool PAIR = false>
 __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __grid_constant__ IgemmParams p,
-                                                                         const __grid_constant__ CUtensorMap amap) {
+                                                                         const __grid_constant__ CUtensorMap amap,
+                                                                         const __grid_constant__ CUtensorMap bmap) {
+  static_assert(!PAIR || (AM == AM_IM2COL && !B_RES), "CTA pairs: im2col producer, streamed B");
   constexpr bool MC_A = AM == AM_MC;
+  constexpr int NCTA = PAIR ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int B_STAGE_BYTES = BN * 128 / NCTA;     // bytes of one B stage in THIS CTA
   constexpr int SROW = stage_row_bytes<BN>();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -98,7 +114,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
   const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
   const uint32_t bres = smem_u32(bars + 2 * STAGES + 4);
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // work unit: one N tile of NCTA consecutive M tiles (one per CTA of the cluster)
+  const int total_tiles = ((p.m_tiles + NCTA - 1) / NCTA) * p.n_tiles;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const bool cta_leader = crank == 0;
+  const int cid = (int)blockIdx.x / NCTA, ncl = (int)gridDim.x / NCTA;
+  auto tile_m0 = [&](int tile) { return ((tile / p.n_tiles) * NCTA + (int)crank) * BM; };
 
   if (warp == 4) {
     if (lane == 0) {
@@ -109,45 +130,93 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(tfull0 + 8 * b, 1);                  // tcgen05.commit after the tile's last MMA
-        mbar_init(tempty0 + 8 * b, 4);                 // one elected lane per epilogue warp
+        mbar_init(tempty0 + 8 * b, 4 * NCTA);          // one elected lane per epilogue warp (of both CTAs)
       }
       mbar_init(bres, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)tmem_cols<BN>())
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)tmem_cols<BN>())
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)tmem_cols<BN>())
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int i = tid; i < p.n_total; i += IG_THREADS) sBias[i] = p.bias_x[i];
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                 // everything above touched only shared memory, TMEM and weights
   pdl_launch_dependents();    // persistent grid: all CTAs are resident, the next kernel may start its prologue
 
   if (AM == AM_IM2COL && warp < 4) {
-    // ===================== im2col TMA producer: one thread issues A (TMA im2col) and B (bulk copy) per stage ==========
-    if (warp == 0 && lane == 0) {
-      tma_prefetch_desc(&amap);
+    // ===================== im2col TMA producers: warp 0 issues the A tile (TMA im2col), warp 1 the B stage ============
+    // Whole warps run the (warp-uniform) loops and only the TMA / barrier instructions are predicated on an elected
+    // lane: operands stay in uniform registers.  (A single-lane loop pays an ELECT + R2UR round trip per operand and
+    // ~500 cycles per stage, more than the MMAs of a stage take.)
+    if (warp == 0) {
+      if (lane == 0) tma_prefetch_desc(&amap);
+      const bool leader = elect_one();
+      int slot = 0;
+      uint32_t par = 1;                                   // parity to wait for on the empty barrier of `slot`
+      long long pw = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+      const long long pbeg = ig_clock();
+      for (int tile = cid; tile < total_tiles; tile += ncl) {
+        const int m0 = tile_m0(tile);
         const int img = fast_div(m0, p.magic_rows), rem = m0 - img * p.rows_per_img;
         const int oy = fast_div(rem, p.magic_wox), ox = rem - oy * p.Wox;
-        int tap = 0, ky = 0, kx = 0, cc = 0;
+        const int w = ox * p.stride, h = oy * p.stride;
+        int ky = 0, kx = 0, cc = 0;
         for (int s = 0; s < p.k_stages; ++s, ++it) {
-          const int slot = it % STAGES;
-          mbar_wait(empty0 + 8 * slot, ((it / STAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(full0 + 8 * slot, (uint32_t)(A_STAGE_BYTES + (B_RES ? 0 : B_STAGE_BYTES)));
-          tma_load_im2col_4d(smem_u32(sA + slot * A_STAGE_BYTES), &amap, cc * 64, ox * p.stride, oy * p.stride, img,
-                             (uint16_t)kx, (uint16_t)ky, full0 + 8 * slot);
-          if (!B_RES)
-            bulk_g2s(smem_u32(sB + slot * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES,
-                     full0 + 8 * slot);
-          if (++cc == p.cin_chunks) { cc = 0; ++tap; if (++kx == p.KW) { kx = 0; ++ky; } }
+          const long long t0 = ig_clock();
+          mbar_wait(empty0 + 8 * slot, par);
+          pw += ig_clock() - t0;
+          if (leader) {
+            if (PAIR) {
+              // both CTAs' A tiles and B halves complete on the leader's barrier, which the leader arms for all four
+              if (cta_leader) mbar_arrive_expect_tx(full0 + 8 * slot, (uint32_t)(2 * (A_STAGE_BYTES + B_STAGE_BYTES)));
+              tma_load_im2col_4d_pair(smem_u32(sA + slot * A_STAGE_BYTES), &amap, cc * 64, w, h, img, (uint16_t)kx, (uint16_t)ky,
+                                      full0 + 8 * slot);
+            } else {
+              mbar_arrive_expect_tx(full0 + 8 * slot, (uint32_t)(A_STAGE_BYTES + (B_RES ? 0 : B_STAGE_BYTES)));
+              tma_load_im2col_4d(smem_u32(sA + slot * A_STAGE_BYTES), &amap, cc * 64, w, h, img, (uint16_t)kx, (uint16_t)ky,
+                                 full0 + 8 * slot);
+            }
+          }
+          __syncwarp();
+          if (++cc == p.cin_chunks) { cc = 0; if (++kx == p.KW) { kx = 0; ++ky; } }
+          if (++slot == STAGES) { slot = 0; par ^= 1u; }
+        }
+      }
+      if (UAHN_IG_PROFILE && p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 0] = pw; p.dbg[blockIdx.x * 16 + 1] = ig_clock() - pbeg; p.dbg[blockIdx.x * 16 + 10] = it; }
+    } else if (warp == 1 && !B_RES) {
+      if (PAIR && lane == 0) tma_prefetch_desc(&bmap);
+      const bool leader = elect_one();
+      int slot = 0;
+      uint32_t par = 1;
+      for (int tile = cid; tile < total_tiles; tile += ncl) {
+        const int n0 = (tile % p.n_tiles) * BN;
+        for (int s = 0; s < p.k_stages; ++s) {
+          mbar_wait(empty0 + 8 * slot, par);
+          if (leader) {
+            if (PAIR)
+              tma_load_2d_pair(smem_u32(sB + slot * B_STAGE_BYTES), &bmap, 0, s * p.n_total + n0 + (int)crank * (BN / 2),
+                               full0 + 8 * slot);
+            else
+              bulk_g2s(smem_u32(sB + slot * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES,
+                       full0 + 8 * slot);
+          }
+          __syncwarp();
+          if (++slot == STAGES) { slot = 0; par ^= 1u; }
         }
       }
     }
@@ -156,8 +225,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
     // thread -> (pair of the tile, granule j of the stage, 8 of the 16 samples); tile = 8 pairs x 16 samples
     const int pl = tid >> 4, j = tid & 7, hs = (tid >> 3) & 1;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.n_tiles) * BM;
+    for (int tile = cid; tile < total_tiles; tile += ncl) {
+      const int m0 = tile_m0(tile);
       const int pair = (m0 >> 4) + pl;
       const bool pvalid = pair * MC < p.M_rows;
       const uint8_t* f = p.in + (size_t)pair * (FC_IN * 2) + j * 16;
@@ -222,8 +291,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
     const int j = tid & 7, rb = tid >> 3;
     const uint32_t dst_off = (uint32_t)rb * 128 + (uint32_t)((j ^ (rb & 7)) << 4);
     int it = 0;                                        // global stage counter (ring position)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.n_tiles) * BM;
+    for (int tile = cid; tile < total_tiles; tile += ncl) {
+      const int m0 = tile_m0(tile);
       uint32_t rowoff[8];
       uint32_t rowok = 0;
 #pragma unroll
@@ -265,22 +334,28 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
     // ===================== MMA issuer =====================
     // The whole warp runs the (warp-uniform) loop control; only the tcgen05 instructions are predicated on the
     // elected lane, so descriptors stay in uniform registers and MMAs issue back to back.
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    constexpr uint32_t idesc = umma_idesc_bf16(BM * NCTA, BN);
     constexpr uint64_t DESC_HI = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t a16_0 = (smem_u32(sA) & 0x3FFFFu) >> 4, b16_0 = (smem_u32(sB) & 0x3FFFFu) >> 4;
     const int k_stages = p.k_stages, k_steps = p.k_steps;
     int it = 0, tcount = 0;
+    long long mw_full = 0, mw_te = 0;
+    const long long mbeg = ig_clock();
     if (B_RES) mbar_wait(bres, 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = cid; tile < (cta_leader ? total_tiles : 0); tile += ncl, ++tcount) {   // the leader issues for the pair
       const int ab = tcount & 1;
+      long long tq = ig_clock();
       mbar_wait(tempty0 + 8 * ab, ((tcount >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+      mw_te += ig_clock() - tq;
       tc_fence_after();
       const uint32_t d_tmem = tmem_u + (uint32_t)(ab * BN);
       const bool leader = elect_one();
       for (int s = 0; s < k_stages; ++s, ++it) {
         const int slot = it % STAGES;
+        tq = ig_clock();
         mbar_wait(full0 + 8 * slot, (it / STAGES) & 1);
+        mw_full += ig_clock() - tq;
         tc_fence_after();
         const uint32_t alo = a16_0 + (uint32_t)(slot * (A_STAGE_BYTES / 16));
         const uint32_t blo = b16_0 + (uint32_t)((B_RES ? s : slot) * (B_STAGE_BYTES / 16));
@@ -288,16 +363,25 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
         if (leader) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)      // +32 B along K inside the swizzle row = +2 in descriptor units
-            if (kk < ksteps)
-              tc_mma_bf16(d_tmem, DESC_HI | (uint64_t)(alo + 2 * kk), DESC_HI | (uint64_t)(blo + 2 * kk), idesc,
-                          (s | kk) != 0 ? 1u : 0u);
-          tc_commit(empty0 + 8 * slot);
-          if (s == k_stages - 1) tc_commit(tfull0 + 8 * ab);
+            if (kk < ksteps) {
+              if (PAIR)
+                tc_mma_bf16_pair(d_tmem, DESC_HI | (uint64_t)(alo + 2 * kk), DESC_HI | (uint64_t)(blo + 2 * kk), idesc,
+                                 (s | kk) != 0 ? 1u : 0u);
+              else
+                tc_mma_bf16(d_tmem, DESC_HI | (uint64_t)(alo + 2 * kk), DESC_HI | (uint64_t)(blo + 2 * kk), idesc,
+                            (s | kk) != 0 ? 1u : 0u);
+            }
+          if (PAIR) tc_commit_pair(empty0 + 8 * slot); else tc_commit(empty0 + 8 * slot);
+          if (s == k_stages - 1) { if (PAIR) tc_commit_pair(tfull0 + 8 * ab); else tc_commit(tfull0 + 8 * ab); }
         }
         __syncwarp();
       }
     }
     tc_fence_before();
+    if (UAHN_IG_PROFILE && p.dbg && lane == 0) {
+      unsigned long long* d = p.dbg + blockIdx.x * 16;
+      d[2] = mw_full; d[3] = mw_te; d[4] = ig_clock() - mbeg; d[9] = tcount;
+    }
   } else if (warp == 5) {
     // ===================== B loader =====================
     if (lane == 0) {
@@ -308,7 +392,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
           bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES, bres);
       } else if (AM != AM_IM2COL) {
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = cid; tile < total_tiles; tile += ncl) {
           const int n0 = (tile % p.n_tiles) * BN;
           for (int s = 0; s < p.k_stages; ++s, ++it) {
             const int slot = it % STAGES;
@@ -328,9 +412,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
     constexpr int CPR = CH / 8;                         // 16-byte chunks per staged row
     constexpr int RPI = 32 / CPR;                       // rows covered by one warp-wide store
     int tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    long long ew = 0, e_ld = 0, e_st = 0;
+    const long long ebeg = ig_clock();
+    for (int tile = cid; tile < total_tiles; tile += ncl, ++tcount) {
       const int ab = tcount & 1;
-      const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+      const int m0 = tile_m0(tile), n0 = (tile % p.n_tiles) * BN;
       {
         const int m = m0 + q * 32 + lane;
         long long off = -1;
@@ -342,11 +428,14 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
         }
         st_shared_b64(row_s + (uint32_t)lane * 8, off);
       }
+      long long tq = ig_clock();
       mbar_wait(tfull0 + 8 * ab, (tcount >> 1) & 1);
+      ew += ig_clock() - tq;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
+        tq = ig_clock();
 #pragma unroll
         for (int c = 0; c < CH / 16; ++c) {
           uint32_t r[16];
@@ -366,10 +455,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
         if (c0 + CH >= BN) {                              // the whole accumulator is in registers / staged
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8 * ab);   // the next tile's MMAs may start
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty0 + 8 * ab); else mbar_arrive(tempty0 + 8 * ab); }   // the next tile's MMAs may start
         } else {
           __syncwarp();
         }
+        e_ld += ig_clock() - tq;
+        tq = ig_clock();
         const int rsub = lane / CPR, ch = lane % CPR;
 #pragma unroll 4
         for (int r0 = 0; r0 < 32; r0 += RPI) {
@@ -379,36 +470,95 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
           if (off >= 0) st_global_v4(p.out + off + c0 * 2 + ch * 16, v.x, v.y, v.z, v.w);
         }
         __syncwarp();
+        e_st += ig_clock() - tq;
       }
     }
+    if (UAHN_IG_PROFILE && p.dbg && warp == 6 && lane == 0) {
+      unsigned long long* d = p.dbg + blockIdx.x * 16;
+      d[5] = ew; d[6] = e_ld; d[7] = e_st; d[8] = ig_clock() - ebeg;
+    }
   }
+  __syncwarp();
+  tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's shared memory and TMEM are in use until the leader's last MMA has retired
   if (warp == 4) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)tmem_cols<BN>())
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols<BN>())
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols<BN>())
+                   : "memory");
   }
 }
 
 template <int BN>
 constexpr size_t fixed_smem() { return 1024 + 128 * (size_t)stage_row_bytes<BN>() + 256 * 4 + 128 * 8 + 64 * 8; }
 
-template <int BN, int STAGES, bool B_RES, int AM = AM_GATHER>
-cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st, const CUtensorMap* amap = nullptr) {
-  const size_t smem = fixed_smem<BN>() + (size_t)STAGES * A_STAGE_BYTES + (size_t)(B_RES ? p.k_stages : STAGES) * BN * 128;
+template <int BN, int STAGES, bool B_RES, int AM = AM_GATHER, bool PAIR = false>
+cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st, const CUtensorMap* amap = nullptr,
+                     const CUtensorMap* bmap = nullptr) {
+  constexpr int NCTA = PAIR ? 2 : 1;
+  const size_t smem =
+      fixed_smem<BN>() + (size_t)STAGES * A_STAGE_BYTES + (size_t)(B_RES ? p.k_stages : STAGES) * (BN * 128 / NCTA);
   if (smem > SMEM_LIMIT) return cudaErrorInvalidConfiguration;
+  auto kern = conv_igemm_bf16_kernel<BN, STAGES, B_RES, AM, PAIR>;
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_bf16_kernel<BN, STAGES, B_RES, AM>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = smem;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
   static const CUtensorMap no_map{};
-  return launch_pdl(conv_igemm_bf16_kernel<BN, STAGES, B_RES, AM>, dim3(std::min(tiles, num_sms)), dim3(IG_THREADS), smem, st, p,
-                    amap ? *amap : no_map);
+  if (!PAIR) {
+    const int tiles = p.m_tiles * p.n_tiles;
+    return launch_pdl(kern, dim3(std::min(tiles, num_sms)), dim3(IG_THREADS), smem, st, p, amap ? *amap : no_map, no_map);
+  }
+  if (!amap || !bmap) return cudaErrorInvalidValue;
+#if UAHN_IG_PROFILE
+  static unsigned long long* d_dbg = nullptr;
+  const bool debug = getenv("UAHN_IG_DEBUG") != nullptr;
+  if (debug && !d_dbg) cudaMalloc(&d_dbg, 16 * 8 * 256);
+  if (debug) cudaMemsetAsync(d_dbg, 0, 16 * 8 * 256, st);
+  IgemmParams pd = p;
+  pd.dbg = debug ? d_dbg : nullptr;
+#else
+  const IgemmParams& pd = p;
+#endif
+  const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;      // one unit = two consecutive M tiles of one N tile
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * std::min(units, num_sms / 2));
+  cfg.blockDim = dim3(IG_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, pd, *amap, *bmap);
+#if UAHN_IG_PROFILE
+  if (debug && le == cudaSuccess) {
+    const int grid = (int)cfg.gridDim.x;
+    std::vector<unsigned long long> h(16 * grid);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+    for (int par = 0; par < 2; ++par) {
+      double a[16] = {0};
+      int cnt = 0;
+      for (int i = par; i < grid; i += 2, ++cnt) for (int j = 0; j < 16; ++j) a[j] += (double)h[i * 16 + j];
+      for (int j = 0; j < 16; ++j) a[j] /= cnt;
+      fprintf(stderr, "[uahn-ig] BN=%d S=%d k_stages=%d m_tiles=%d %s: stages/CTA %.1f tiles/CTA %.1f | producer wait_empty %.0f of %.0f | mma wait_full %.0f wait_tempty %.0f of %.0f | epi wait_tfull %.0f ld+pack %.0f store %.0f of %.0f (cycles per CTA)\n",
+              BN, STAGES, p.k_stages, p.m_tiles, par ? "peer  " : "leader", a[10], a[9], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]);
+    }
+  }
+#endif
+  return le;
 }
 
 }  // namespace
@@ -516,6 +666,29 @@ int conv_bf16_prepare(ConvBf16Weights& wb, const std::vector<float>& wk, const s
                                 gstr, lower, upper, 64, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       wb.im2col = r == CUDA_SUCCESS;
+      // CTA-pair mode streams each CTA's half of a B stage through a plain 2-D tiled map over the pre-swizzled image
+      // (rows of 128 bytes, copied verbatim: no swizzle in the map)
+      static PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
+      if (!encode_tiled) {
+        void* fp2 = nullptr;
+        cudaDriverEntryPointQueryResult q2;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp2, cudaEnableDefault, &q2) == cudaSuccess &&
+            q2 == cudaDriverEntryPointSuccess)
+          encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fp2);
+      }
+      wb.pair_ok = wb.im2col && encode_tiled && !getenv("UAHN_NO_IGEMM_PAIR");
+      for (int i = 0; i < 3 && wb.pair_ok; ++i) {
+        const int rows = 128 >> i;
+        if (rows * 2 > n_total) { memset(wb.b_half_map[i], 0, 128); continue; }
+        const cuuint64_t bdim[2] = {64, (cuuint64_t)k_stages * n_total};
+        const cuuint64_t bstr[1] = {128};
+        const cuuint32_t bbox[2] = {64, (cuuint32_t)rows};
+        const cuuint32_t bes[2] = {1, 1};
+        const CUresult rb = encode_tiled(reinterpret_cast<CUtensorMap*>(wb.b_half_map[i]), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d,
+                                         bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rb != CUDA_SUCCESS) wb.pair_ok = 0;
+      }
       if (getenv("UAHN_DEBUG"))
         fprintf(stderr, "[uahn] im2col TMA map Cin=%d k=%d s=%d out=%dx%d: W'=%d H'=%d upper=(%d,%d) -> %s\n", g.Cin, g.KH, s_,
                 g.Ho, g.Wo, Wt, Ht, upper[0], upper[1], wb.im2col ? "ok" : "encode failed, cp.async gather");
@@ -611,6 +784,15 @@ cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const fl
   if (wb.im2col) {
     p.Ho = g.Ho; p.stride = g.stride; p.KW = g.KW; p.cin_chunks = g.Cin / 64;
     const CUtensorMap* am = reinterpret_cast<const CUtensorMap*>(wb.im2col_map);
+    // enough tiles to fill the machine: CTA pairs (half the B bytes per SM and tile)
+    if (wb.pair_ok && (long long)p.m_tiles * p.n_tiles >= num_sms) {
+      switch (bn) {
+        case 256: return launch_t<256, 6, false, AM_IM2COL, true>(p, num_sms, st, am, reinterpret_cast<const CUtensorMap*>(wb.b_half_map[0]));
+        case 128: return launch_t<128, 8, false, AM_IM2COL, true>(p, num_sms, st, am, reinterpret_cast<const CUtensorMap*>(wb.b_half_map[1]));
+        case 64: return launch_t<64, 8, false, AM_IM2COL, true>(p, num_sms, st, am, reinterpret_cast<const CUtensorMap*>(wb.b_half_map[2]));
+        default: break;
+      }
+    }
     switch (bn) {
       case 256: return launch_t<256, 4, false, AM_IM2COL>(p, num_sms, st, am);
       case 128: return res ? launch_t<128, 5, true, AM_IM2COL>(p, num_sms, st, am) : launch_t<128, 6, false, AM_IM2COL>(p, num_sms, st, am);

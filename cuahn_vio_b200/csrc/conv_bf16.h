@@ -48,6 +48,9 @@ struct ConvBf16Weights {
   // im2col TMA A producer (conv_bf16.cu, Cin % 64 == 0 layers): tensor map over the haloed NHWC input
   int im2col = 0;
   alignas(64) unsigned char im2col_map[128];
+  // CTA-pair mode: tiled tensor maps over the pre-swizzled B image with boxes of 128 / 64 / 32 rows (half an N tile)
+  int pair_ok = 0;
+  alignas(64) unsigned char b_half_map[3][128];
 };
 
 // wk: [K][Cout] fp32 with k = (ky*KW + kx)*Cin + c.  Appends device allocations to `allocs`.
