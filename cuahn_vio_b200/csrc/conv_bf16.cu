@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   static_assert(!PAIR || (AM == AM_IM2COL && !B_RES), "CTA pairs: im2col producer, streamed B");
   constexpr bool MC_A = AM == AM_MC;
   constexpr int NCTA = PAIR ? 2 : 1;
+  const long long k_entry = ig_clock();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * 128 / NCTA;     // bytes of one B stage in THIS CTA
   constexpr int SROW = stage_row_bytes<BN>();
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                 // everything above touched only shared memory, TMEM and weights
   pdl_launch_dependents();    // persistent grid: all CTAs are resident, the next kernel may start its prologue
+  const long long k_roles = ig_clock();
 
   if (AM == AM_IM2COL && warp < 4) {
     // ===================== im2col TMA producers: warp 0 issues the A tile (TMA im2col), warp 1 the B stage ============
@@ -225,6 +227,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
     // thread -> (pair of the tile, granule j of the stage, 8 of the 16 samples); tile = 8 pairs x 16 samples
     const int pl = tid >> 4, j = tid & 7, hs = (tid >> 3) & 1;
     int it = 0;
+    long long pw = 0;
+    const long long pbeg = ig_clock();
     for (int tile = cid; tile < total_tiles; tile += ncl) {
       const int m0 = tile_m0(tile);
       const int pair = (m0 >> 4) + pl;
@@ -266,7 +270,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
               sc[c] = pack_bf16x2(lo, hi);
             }
           }
+          const long long t0 = ig_clock();
           mbar_wait(empty0 + 8 * slot, ((it / STAGES) & 1) ^ 1);
+          pw += ig_clock() - t0;
           const uint32_t stage = smem_u32(sA + slot * A_STAGE_BYTES);
 #pragma unroll
           for (int si = 0; si < 8; ++si) {
@@ -286,6 +292,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
         }
       }
     }
+    if (UAHN_IG_PROFILE && p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = pw; p.dbg[blockIdx.x * 16 + 1] = ig_clock() - pbeg; p.dbg[blockIdx.x * 16 + 10] = it; }
   } else if (warp < 4) {
     // ===================== A gather: 128 threads, 8 rows x 1 granule column each per stage ==============
     const int j = tid & 7, rb = tid >> 3;
@@ -383,26 +390,37 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
       d[2] = mw_full; d[3] = mw_te; d[4] = ig_clock() - mbeg; d[9] = tcount;
     }
   } else if (warp == 5) {
-    // ===================== B loader =====================
-    if (lane == 0) {
-      if (B_RES) {
-        const int n0 = (blockIdx.x % p.n_tiles) * BN;   // resident mode is launched with n_tiles == 1
+    // ===================== B loader (gather / MC modes; the im2col mode loads B from warp 1) =====================
+    // warp-uniform loop, the copies predicated on one elected lane (see the im2col producers)
+    const bool leader = elect_one();
+    if (B_RES) {
+      const int n0 = (blockIdx.x % p.n_tiles) * BN;   // resident mode is launched with n_tiles == 1
+      if (leader) {
         mbar_arrive_expect_tx(bres, (uint32_t)(p.k_stages * B_STAGE_BYTES));
         for (int s = 0; s < p.k_stages; ++s)
           bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES, bres);
-      } else if (AM != AM_IM2COL) {
-        int it = 0;
-        for (int tile = cid; tile < total_tiles; tile += ncl) {
-          const int n0 = (tile % p.n_tiles) * BN;
-          for (int s = 0; s < p.k_stages; ++s, ++it) {
-            const int slot = it % STAGES;
-            mbar_wait(empty0 + 8 * slot, ((it / STAGES) & 1) ^ 1);
+      }
+    } else if (AM != AM_IM2COL) {
+      int slot = 0;
+      uint32_t par = 1;
+      long long bw = 0;
+      const long long bbeg = ig_clock();
+      for (int tile = cid; tile < total_tiles; tile += ncl) {
+        const int n0 = (tile % p.n_tiles) * BN;
+        for (int s = 0; s < p.k_stages; ++s) {
+          const long long t0 = ig_clock();
+          mbar_wait(empty0 + 8 * slot, par);
+          bw += ig_clock() - t0;
+          if (leader) {
             mbar_arrive_expect_tx(full0 + 8 * slot, B_STAGE_BYTES);
-            bulk_g2s(smem_u32(sB + slot * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128,
-                     B_STAGE_BYTES, full0 + 8 * slot);
+            bulk_g2s(smem_u32(sB + slot * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES,
+                     full0 + 8 * slot);
           }
+          __syncwarp();
+          if (++slot == STAGES) { slot = 0; par ^= 1u; }
         }
       }
+      if (UAHN_IG_PROFILE && p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 11] = bw; p.dbg[blockIdx.x * 16 + 12] = ig_clock() - bbeg; }
     }
   } else {
     // ===================== epilogue (warps 6-9): TMEM -> bias/LeakyReLU -> bf16 -> smem -> coalesced global ====
@@ -482,6 +500,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();   // the peer's shared memory and TMEM are in use until the leader's last MMA has retired
+  if (UAHN_IG_PROFILE && p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 13] = k_roles - k_entry; p.dbg[blockIdx.x * 16 + 14] = ig_clock() - k_entry; }
   if (warp == 4) {
     tc_fence_after();
     if (PAIR)
@@ -511,11 +530,7 @@ cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st, const C
     attr = smem;
   }
   static const CUtensorMap no_map{};
-  if (!PAIR) {
-    const int tiles = p.m_tiles * p.n_tiles;
-    return launch_pdl(kern, dim3(std::min(tiles, num_sms)), dim3(IG_THREADS), smem, st, p, amap ? *amap : no_map, no_map);
-  }
-  if (!amap || !bmap) return cudaErrorInvalidValue;
+  if (PAIR && (!amap || !bmap)) return cudaErrorInvalidValue;
 #if UAHN_IG_PROFILE
   static unsigned long long* d_dbg = nullptr;
   const bool debug = getenv("UAHN_IG_DEBUG") != nullptr;
@@ -526,35 +541,37 @@ cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st, const C
 #else
   const IgemmParams& pd = p;
 #endif
-  const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;      // one unit = two consecutive M tiles of one N tile
+  // PAIR: one unit = two consecutive M tiles of one N tile, one cluster of two CTAs per unit
+  const int units = ((p.m_tiles + NCTA - 1) / NCTA) * p.n_tiles;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * std::min(units, num_sms / 2));
+  cfg.gridDim = dim3(NCTA * std::min(units, num_sms / NCTA));
   cfg.blockDim = dim3(IG_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.x = NCTA;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, pd, *amap, *bmap);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, pd, amap ? *amap : no_map, bmap ? *bmap : no_map);
 #if UAHN_IG_PROFILE
   if (debug && le == cudaSuccess) {
     const int grid = (int)cfg.gridDim.x;
     std::vector<unsigned long long> h(16 * grid);
     cudaStreamSynchronize(st);
     cudaMemcpy(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
-    for (int par = 0; par < 2; ++par) {
+    for (int par = 0; par < NCTA; ++par) {
       double a[16] = {0};
       int cnt = 0;
-      for (int i = par; i < grid; i += 2, ++cnt) for (int j = 0; j < 16; ++j) a[j] += (double)h[i * 16 + j];
+      for (int i = par; i < grid; i += NCTA, ++cnt) for (int j = 0; j < 16; ++j) a[j] += (double)h[i * 16 + j];
       for (int j = 0; j < 16; ++j) a[j] /= cnt;
-      fprintf(stderr, "[uahn-ig] BN=%d S=%d k_stages=%d m_tiles=%d %s: stages/CTA %.1f tiles/CTA %.1f | producer wait_empty %.0f of %.0f | mma wait_full %.0f wait_tempty %.0f of %.0f | epi wait_tfull %.0f ld+pack %.0f store %.0f of %.0f (cycles per CTA)\n",
-              BN, STAGES, p.k_stages, p.m_tiles, par ? "peer  " : "leader", a[10], a[9], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]);
+      fprintf(stderr, "[uahn-ig] BN=%d S=%d AM=%d k_stages=%d m_tiles=%d %s: stages/CTA %.1f tiles/CTA %.1f | producer wait_empty %.0f of %.0f | B loader wait_empty %.0f of %.0f | mma wait_full %.0f wait_tempty %.0f of %.0f | epi wait_tfull %.0f ld+pack %.0f store %.0f of %.0f (cycles per CTA) | prologue %.0f kernel %.0f\n",
+              BN, STAGES, AM, p.k_stages, p.m_tiles, !PAIR ? "" : par ? "peer  " : "leader", a[10], a[9], a[0], a[1], a[11], a[12], a[2], a[3], a[4], a[5],
+              a[6], a[7], a[8], a[13], a[14]);
     }
   }
 #endif

@@ -363,6 +363,29 @@ def test_fused_front_matches_per_layer_kernels(api, wfile):
     assert np.abs(outs[True][0] - outs[False][0]).max() < BF16_PX
 
 
+def test_cta_pair_deep_layers_match_single_cta_kernels(api, wfile):
+    """Deep conv layers (Cin % 64 == 0) at a batch large enough for the CTA-pair kernels (tcgen05.mma.cta_group::2, half
+    of each B stage per CTA) vs the one-CTA im2col kernels: the same accumulation order, so every activation and output
+    is bit-identical.  1090 pairs -> 171 M tiles in the last layers: the odd count leaves the peer CTA of the last
+    unit with a tile entirely past the end of M."""
+    import os
+    n = 1090
+    prev, curr, _, prior = S.tiled_batch(n, unique=8)
+    outs = {}
+    for pair in (True, False):
+        if not pair:
+            os.environ["UAHN_NO_IGEMM_PAIR"] = "1"
+        try:
+            with api.Uahn(wfile, "prior3", precision="bf16", max_batch=n) as net:
+                m, c, _ = net.infer_batch(prev, curr, prior, seed=8)
+                outs[pair] = (m, c, net.debug_read("feat4", (n, 256, 4, 5)), net.debug_read("act:block_2_2", (n, 128, 14, 20)))
+        finally:
+            os.environ.pop("UAHN_NO_IGEMM_PAIR", None)
+    for a, b in zip(outs[True], outs[False]):
+        assert np.array_equal(a, b)
+    assert np.isfinite(outs[True][0]).all() and np.abs(outs[True][2]).max() > 0
+
+
 def test_edge_inputs_fp32_vs_oracle(api, wfile, synth_sd):
     """Degenerate frames and a prior that throws the warp (mostly) outside the image: black, saturated, identical
     frames, a 250-px shift; n == max_batch and n < max_batch through the same handle."""
