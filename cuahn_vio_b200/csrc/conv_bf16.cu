@@ -93,7 +93,7 @@ template <int BN, int STAGES, bool B_RES, int AM = AM_GATHER, bool PAIR = false>
 __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __grid_constant__ IgemmParams p,
                                                                          const __grid_constant__ CUtensorMap amap,
                                                                          const __grid_constant__ CUtensorMap bmap) {
-  static_assert(!PAIR || (AM == AM_IM2COL && !B_RES), "CTA pairs: im2col producer, streamed B");
+  static_assert(!PAIR || (AM != AM_GATHER && !B_RES), "CTA pairs: im2col or MC producer, streamed B");
   constexpr bool MC_A = AM == AM_MC;
   constexpr int NCTA = PAIR ? 2 : 1;
   const long long k_entry = ig_clock();
@@ -125,8 +125,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
-        // 128 producer threads (+ the B loader's expect_tx arrive); im2col: one arrive.expect_tx for A and B together
-        mbar_init(full0 + 8 * s, AM == AM_IM2COL ? 1 : (B_RES ? 128 : 129));
+        // im2col: one arrive.expect_tx for A and B together; MC: one arrive per producer warp (of both CTAs) + the B
+        // loader's expect_tx; gather: 128 producer threads (+ the B loader)
+        mbar_init(full0 + 8 * s, AM == AM_IM2COL ? 1 : MC_A ? 4 * NCTA + 1 : (B_RES ? 128 : 129));
         mbar_init(empty0 + 8 * s, 1);                  // one tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
@@ -287,7 +288,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
             st_shared_v4(stage + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)), o[0], o[1], o[2], o[3]);
           }
           fence_proxy_async();                          // generic-proxy writes -> visible to the UMMA reads
-          mbar_arrive(full0 + 8 * slot);
+          __syncwarp();
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(full0 + 8 * slot); else mbar_arrive(full0 + 8 * slot); }
           ++it;
         }
       }
@@ -393,6 +395,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
     // ===================== B loader (gather / MC modes; the im2col mode loads B from warp 1) =====================
     // warp-uniform loop, the copies predicated on one elected lane (see the im2col producers)
     const bool leader = elect_one();
+    if (PAIR && lane == 0) tma_prefetch_desc(&bmap);
     if (B_RES) {
       const int n0 = (blockIdx.x % p.n_tiles) * BN;   // resident mode is launched with n_tiles == 1
       if (leader) {
@@ -412,9 +415,15 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
           mbar_wait(empty0 + 8 * slot, par);
           bw += ig_clock() - t0;
           if (leader) {
-            mbar_arrive_expect_tx(full0 + 8 * slot, B_STAGE_BYTES);
-            bulk_g2s(smem_u32(sB + slot * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES,
-                     full0 + 8 * slot);
+            if (PAIR) {   // both halves complete on the leader CTA's barrier
+              if (cta_leader) mbar_arrive_expect_tx(full0 + 8 * slot, 2 * B_STAGE_BYTES);
+              tma_load_2d_pair(smem_u32(sB + slot * B_STAGE_BYTES), &bmap, 0, s * p.n_total + n0 + (int)crank * (BN / 2),
+                               full0 + 8 * slot);
+            } else {
+              mbar_arrive_expect_tx(full0 + 8 * slot, B_STAGE_BYTES);
+              bulk_g2s(smem_u32(sB + slot * B_STAGE_BYTES), p.b_image + ((size_t)s * p.n_total + n0) * 128, B_STAGE_BYTES,
+                       full0 + 8 * slot);
+            }
           }
           __syncwarp();
           if (++slot == STAGES) { slot = 0; par ^= 1u; }
@@ -530,7 +539,7 @@ cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st, const C
     attr = smem;
   }
   static const CUtensorMap no_map{};
-  if (PAIR && (!amap || !bmap)) return cudaErrorInvalidValue;
+  if (PAIR && (!bmap || (AM == AM_IM2COL && !amap))) return cudaErrorInvalidValue;
 #if UAHN_IG_PROFILE
   static unsigned long long* d_dbg = nullptr;
   const bool debug = getenv("UAHN_IG_DEBUG") != nullptr;
@@ -683,32 +692,34 @@ int conv_bf16_prepare(ConvBf16Weights& wb, const std::vector<float>& wk, const s
                                 gstr, lower, upper, 64, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       wb.im2col = r == CUDA_SUCCESS;
-      // CTA-pair mode streams each CTA's half of a B stage through a plain 2-D tiled map over the pre-swizzled image
-      // (rows of 128 bytes, copied verbatim: no swizzle in the map)
-      static PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
-      if (!encode_tiled) {
-        void* fp2 = nullptr;
-        cudaDriverEntryPointQueryResult q2;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp2, cudaEnableDefault, &q2) == cudaSuccess &&
-            q2 == cudaDriverEntryPointSuccess)
-          encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fp2);
-      }
-      wb.pair_ok = wb.im2col && encode_tiled && !getenv("UAHN_NO_IGEMM_PAIR");
-      for (int i = 0; i < 3 && wb.pair_ok; ++i) {
-        const int rows = 128 >> i;
-        if (rows * 2 > n_total) { memset(wb.b_half_map[i], 0, 128); continue; }
-        const cuuint64_t bdim[2] = {64, (cuuint64_t)k_stages * n_total};
-        const cuuint64_t bstr[1] = {128};
-        const cuuint32_t bbox[2] = {64, (cuuint32_t)rows};
-        const cuuint32_t bes[2] = {1, 1};
-        const CUresult rb = encode_tiled(reinterpret_cast<CUtensorMap*>(wb.b_half_map[i]), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d,
-                                         bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (rb != CUDA_SUCCESS) wb.pair_ok = 0;
-      }
       if (getenv("UAHN_DEBUG"))
         fprintf(stderr, "[uahn] im2col TMA map Cin=%d k=%d s=%d out=%dx%d: W'=%d H'=%d upper=(%d,%d) -> %s\n", g.Cin, g.KH, s_,
                 g.Ho, g.Wo, Wt, Ht, upper[0], upper[1], wb.im2col ? "ok" : "encode failed, cp.async gather");
+    }
+  }
+  // CTA-pair mode streams each CTA's half of a B stage through a plain 2-D tiled map over the pre-swizzled image
+  // (rows of 128 bytes, copied verbatim: no swizzle in the map)
+  {
+    static PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
+    if (!encode_tiled) {
+      void* fp2 = nullptr;
+      cudaDriverEntryPointQueryResult q2;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp2, cudaEnableDefault, &q2) == cudaSuccess &&
+          q2 == cudaDriverEntryPointSuccess)
+        encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fp2);
+    }
+    wb.pair_ok = encode_tiled && n_total >= 64 && !getenv("UAHN_NO_IGEMM_PAIR");
+    for (int i = 0; i < 3 && wb.pair_ok; ++i) {
+      const int rows = 128 >> i;
+      if (rows * 2 > n_total) { memset(wb.b_half_map[i], 0, 128); continue; }
+      const cuuint64_t bdim[2] = {64, (cuuint64_t)k_stages * n_total};
+      const cuuint64_t bstr[1] = {128};
+      const cuuint32_t bbox[2] = {64, (cuuint32_t)rows};
+      const cuuint32_t bes[2] = {1, 1};
+      const CUresult rb = encode_tiled(reinterpret_cast<CUtensorMap*>(wb.b_half_map[i]), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d,
+                                       bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rb != CUDA_SUCCESS) wb.pair_ok = 0;
     }
   }
   wb.b_image = d;
@@ -749,6 +760,11 @@ cudaError_t launch_mc_gemm_bf16(const ConvBf16Weights& wb, const void* feat, con
   p.act = 1;
   p.m_tiles = (p.M_rows + BM - 1) / BM;
   p.n_tiles = 1;
+  // CTA pairs (two consecutive 8-pair M tiles share every UMMA, half of each weight stage per CTA) once there are
+  // enough tiles: the one-CTA kernel is bound by shared-memory bandwidth (16 KB of A + 32 KB of B written and 48 KB read
+  // by the tensor core per stage), the pair moves a third less
+  if (wb.pair_ok && p.m_tiles >= 32)
+    return launch_t<256, 6, false, AM_MC, true>(p, num_sms, st, nullptr, reinterpret_cast<const CUtensorMap*>(wb.b_half_map[0]));
   return launch_t<256, 4, false, AM_MC>(p, num_sms, st);
 }
 
@@ -802,7 +818,7 @@ cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const fl
     p.Ho = g.Ho; p.stride = g.stride; p.KW = g.KW; p.cin_chunks = g.Cin / 64;
     const CUtensorMap* am = reinterpret_cast<const CUtensorMap*>(wb.im2col_map);
     // enough tiles to fill the machine: CTA pairs (half the B bytes per SM and tile)
-    if (wb.pair_ok && (long long)p.m_tiles * p.n_tiles >= num_sms) {
+    if (wb.im2col && wb.pair_ok && (long long)p.m_tiles * p.n_tiles >= num_sms) {
       switch (bn) {
         case 256: return launch_t<256, 6, false, AM_IM2COL, true>(p, num_sms, st, am, reinterpret_cast<const CUtensorMap*>(wb.b_half_map[0]));
         case 128: return launch_t<128, 8, false, AM_IM2COL, true>(p, num_sms, st, am, reinterpret_cast<const CUtensorMap*>(wb.b_half_map[1]));
