@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
-        // im2col: one arrive.expect_tx for A and B together; MC: one arrive per producer warp (of both CTAs) + the B
+        // im2col: one arrive.expect_tx for A and B together; MC: the stage's producer warp (of each CTA) + the B
         // loader's expect_tx; gather: 128 producer threads (+ the B loader)
-        mbar_init(full0 + 8 * s, AM == AM_IM2COL ? 1 : MC_A ? 4 * NCTA + 1 : (B_RES ? 128 : 129));
+        mbar_init(full0 + 8 * s, AM == AM_IM2COL ? 1 : MC_A ? NCTA + 1 : (B_RES ? 128 : 129));
         mbar_init(empty0 + 8 * s, 1);                  // one tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
@@ -225,76 +225,80 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
     }
   } else if (MC_A && warp < 4) {
     // ===================== masked-feature producer (MC-dropout GEMM) =====================
-    // thread -> (pair of the tile, granule j of the stage, 8 of the 16 samples); tile = 8 pairs x 16 samples
-    const int pl = tid >> 4, j = tid & 7, hs = (tid >> 3) & 1;
-    int it = 0;
+    // Producer warp w builds every 4th stage (global stage counter it = w mod 4) on its own, so four stages are under
+    // construction at once: the per-stage chain wait(empty) -> stores -> fence.proxy.async -> arrive is latency-, not
+    // issue-bound, and four warps working on the SAME stage ran it once per ~800 cycles.
+    // lane -> (granule j of the stage, pair group pg); the lane handles pairs pg and pg + 4 of the tile's 8, all 16 samples.
+    const int j = lane & 7, pg = lane >> 3;
+    const int my_tiles = total_tiles > cid ? (total_tiles - cid + ncl - 1) / ncl : 0;
+    const int n_it = my_tiles * p.k_stages;
     long long pw = 0;
     const long long pbeg = ig_clock();
-    for (int tile = cid; tile < total_tiles; tile += ncl) {
-      const int m0 = tile_m0(tile);
-      const int pair = (m0 >> 4) + pl;
-      const bool pvalid = pair * MC < p.M_rows;
-      const uint8_t* f = p.in + (size_t)pair * (FC_IN * 2) + j * 16;
-      const uint8_t* mb = p.mc_bits + ((size_t)pair * (FC_IN / 8) + j) * MC + hs * 8;
-      // feature granule + mask bytes are fetched two stages ahead (L2 latency is several stage times)
-      constexpr int PF = 2;
-      uint4 gq[PF];
-      uint2 mq[PF];
+    auto src = [&](int it, int pp, const uint8_t*& f, const uint8_t*& mb) -> bool {
+      const int tl = it / p.k_stages, st = it - tl * p.k_stages;
+      const int pair = (tile_m0(cid + tl * ncl) >> 4) + pg + 4 * pp;
+      f = p.in + (size_t)pair * (FC_IN * 2) + (size_t)st * 128 + j * 16;
+      mb = p.mc_bits + ((size_t)pair * (FC_IN / 8) + (size_t)st * 8 + j) * MC;
+      return pair * MC < p.M_rows;
+    };
+    uint4 gq[2], mq[2];                                   // this warp's next stage, fetched one round (4 stages) ahead
 #pragma unroll
-      for (int d = 0; d < PF; ++d) {
-        gq[d] = make_uint4(0u, 0u, 0u, 0u);
-        mq[d] = make_uint2(0u, 0u);
-        if (pvalid && d < p.k_stages) {
-          gq[d] = __ldg(reinterpret_cast<const uint4*>(f + (size_t)d * 128));
-          mq[d] = __ldg(reinterpret_cast<const uint2*>(mb + (size_t)d * 8 * MC));
-        }
-      }
-      for (int s0 = 0; s0 < p.k_stages; s0 += PF) {
-#pragma unroll
-        for (int d = 0; d < PF; ++d) {
-          const int s = s0 + d;
-          if (s >= p.k_stages) break;
-          const int slot = it % STAGES;
-          const uint4 g = gq[d];
-          const uint2 mk = mq[d];
-          if (pvalid && s + PF < p.k_stages) {
-            gq[d] = __ldg(reinterpret_cast<const uint4*>(f + (size_t)(s + PF) * 128));
-            mq[d] = __ldg(reinterpret_cast<const uint2*>(mb + (size_t)(s + PF) * 8 * MC));
-          }
-          // kept values are scaled by 1/0.95 in fp32 and rounded to bf16 once per pair (same rounding as mc_expand)
-          uint32_t sc[4];
-          {
-            const uint32_t w[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float lo = __uint_as_float(w[c] << 16) * KEEP_SCALE, hi = __uint_as_float(w[c] & 0xFFFF0000u) * KEEP_SCALE;
-              sc[c] = pack_bf16x2(lo, hi);
-            }
-          }
-          const long long t0 = ig_clock();
-          mbar_wait(empty0 + 8 * slot, ((it / STAGES) & 1) ^ 1);
-          pw += ig_clock() - t0;
-          const uint32_t stage = smem_u32(sA + slot * A_STAGE_BYTES);
-#pragma unroll
-          for (int si = 0; si < 8; ++si) {
-            const uint32_t bits = ((si < 4 ? mk.x : mk.y) >> (8 * (si & 3))) & 0xFFu;
-            uint32_t o[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t b2 = bits >> (2 * c);
-              o[c] = sc[c] & (((b2 & 1u) ? 0x0000FFFFu : 0u) | ((b2 & 2u) ? 0xFFFF0000u : 0u));
-            }
-            const int r = pl * MC + hs * 8 + si;
-            st_shared_v4(stage + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)), o[0], o[1], o[2], o[3]);
-          }
-          fence_proxy_async();                          // generic-proxy writes -> visible to the UMMA reads
-          __syncwarp();
-          if (lane == 0) { if (PAIR) mbar_arrive_leader(full0 + 8 * slot); else mbar_arrive(full0 + 8 * slot); }
-          ++it;
-        }
+    for (int pp = 0; pp < 2; ++pp) {
+      gq[pp] = mq[pp] = make_uint4(0u, 0u, 0u, 0u);
+      const uint8_t *f, *mb;
+      if (warp < n_it && src(warp, pp, f, mb)) {
+        gq[pp] = __ldg(reinterpret_cast<const uint4*>(f));
+        mq[pp] = __ldg(reinterpret_cast<const uint4*>(mb));
       }
     }
-    if (UAHN_IG_PROFILE && p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = pw; p.dbg[blockIdx.x * 16 + 1] = ig_clock() - pbeg; p.dbg[blockIdx.x * 16 + 10] = it; }
+    for (int it = warp; it < n_it; it += 4) {
+      const int slot = it % STAGES;
+      uint4 g[2] = {gq[0], gq[1]}, mk[2] = {mq[0], mq[1]};
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        gq[pp] = mq[pp] = make_uint4(0u, 0u, 0u, 0u);
+        const uint8_t *f, *mb;
+        if (it + 4 < n_it && src(it + 4, pp, f, mb)) {
+          gq[pp] = __ldg(reinterpret_cast<const uint4*>(f));
+          mq[pp] = __ldg(reinterpret_cast<const uint4*>(mb));
+        }
+      }
+      // kept values are scaled by 1/0.95 in fp32 and rounded to bf16 once per pair (same rounding as mc_expand)
+      uint32_t sc[2][4];
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        const uint32_t w[4] = {g[pp].x, g[pp].y, g[pp].z, g[pp].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float lo = __uint_as_float(w[c] << 16) * KEEP_SCALE, hi = __uint_as_float(w[c] & 0xFFFF0000u) * KEEP_SCALE;
+          sc[pp][c] = pack_bf16x2(lo, hi);
+        }
+      }
+      const long long t0 = ig_clock();
+      mbar_wait(empty0 + 8 * slot, ((it / STAGES) & 1) ^ 1);
+      pw += ig_clock() - t0;
+      const uint32_t stage = smem_u32(sA + slot * A_STAGE_BYTES);
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        const uint32_t mw[4] = {mk[pp].x, mk[pp].y, mk[pp].z, mk[pp].w};
+#pragma unroll
+        for (int si = 0; si < MC; ++si) {
+          const uint32_t bits = (mw[si >> 2] >> (8 * (si & 3))) & 0xFFu;
+          uint32_t o[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t b2 = bits >> (2 * c);
+            o[c] = sc[pp][c] & (((b2 & 1u) ? 0x0000FFFFu : 0u) | ((b2 & 2u) ? 0xFFFF0000u : 0u));
+          }
+          const int r = (pg + 4 * pp) * MC + si;
+          st_shared_v4(stage + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)), o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_proxy_async();                          // generic-proxy writes -> visible to the UMMA reads
+      __syncwarp();
+      if (lane == 0) { if (PAIR) mbar_arrive_leader(full0 + 8 * slot); else mbar_arrive(full0 + 8 * slot); }
+    }
+    if (UAHN_IG_PROFILE && p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = pw; p.dbg[blockIdx.x * 16 + 1] = ig_clock() - pbeg; p.dbg[blockIdx.x * 16 + 10] = n_it; }
   } else if (warp < 4) {
     // ===================== A gather: 128 threads, 8 rows x 1 granule column each per stage ==============
     const int j = tid & 7, rb = tid >> 3;
