@@ -12,10 +12,14 @@
 //   Cout = 8/16/32 layers fill a 128 x N tensor-core tile: N = XB*Cout.
 // * B (weights) is prepared once on the host as the exact shared-memory image of every K stage, so a stage
 //   is one cp.async.bulk (TMA bulk copy, UBLKCP) completing on the stage's mbarrier.
-// * Warp roles: warps 0-3 gather A (or, MC_A, build the MC-dropout expansion of the block-4 feature on the fly),
-//   warp 4 issues tcgen05.mma from one elected lane, warp 5 streams B, warps 6-9 run the epilogue (tcgen05.ld ->
-//   bias -> bf16 -> LeakyReLU -> 64-column staging -> coalesced global).  Full/empty mbarriers per stage;
-//   tcgen05.commit releases a stage when the MMAs that read it retire.
+// * Warp roles: warps 0-3 produce A — cp.async gather; or (AM_IM2COL) warp 0 issues one im2col-mode TMA load per stage
+//   and warp 1 the B stage; or (AM_MC) each warp builds every 4th stage of the MC-dropout expansion of the block-4
+//   feature on the fly.  Warp 4 issues tcgen05.mma from one elected lane, warp 5 streams B (gather / MC modes), warps
+//   6-9 run the epilogue (tcgen05.ld -> bias -> bf16 -> LeakyReLU -> 64-column staging -> coalesced global).
+//   Full/empty mbarriers per stage; tcgen05.commit releases a stage when the MMAs that read it retire.
+// * PAIR: clusters of two CTAs share every UMMA (cta_group::2, M = 256) and split each B stage between them.
+// * All TMA / bulk-copy issue loops are warp-uniform with the copy predicated on an elected lane (a single-lane loop
+//   costs ~500 cycles per stage in ELECT / R2UR.BROADCAST round trips).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
