@@ -37,6 +37,8 @@ namespace {
 
 constexpr int EPI_WARPS = 16;             // 4 per TMEM lane quadrant; each takes BN/4 accumulator columns
 constexpr int TM_THREADS = 64 + 32 * EPI_WARPS;
+// epilogue staging: [2 buffers][4 TMEM lane quadrants][32 rows][128 B of bf16 + 16 B pad]
+constexpr int EPI_ROW = 144, EPI_STAGE_BYTES = 2 * 4 * 32 * EPI_ROW;
 constexpr int MAX_SLOTS = 12;
 constexpr int MAX_OPS = 128;              // tcgen05.mma instructions per tile (KH taps x chunks x k-steps)
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
   // bars: [0,S) full, [S,2S) empty, 2S..2S+1 accumulator full, 2S+2..2S+3 accumulator empty, 2S+4 B resident
   const int S = p.n_slots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 5);
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(bars + 2 * MAX_SLOTS + 8) + 16 * 4;   // epilogue staging (16-byte aligned)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_SLOTS);
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
   static_assert(COLS == 16, "epilogue is written for 16 accumulator columns per warp");
   const int q = warp & 3, cg = (warp - 2) >> 2;         // TMEM lane quadrant (hardware rule), column group
   const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * COLS);
+  const uint32_t stage_s = smem_u32(sStage);
   uint32_t biasu[COLS];
   if (warp >= 2) {
 #pragma unroll
@@ -133,28 +137,40 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // warp-uniform loop, the TMA / barrier instructions predicated on one elected lane: coordinates and barrier
+    // addresses stay in uniform registers (a single-lane loop pays an ELECT / R2UR.BROADCAST round trip per operand —
+    // several hundred cycles per load, more than the 18 MMAs of a tile take)
+    const bool leader = elect_one();
+    if (leader) {
       tma_prefetch_desc(&tmap);
       mbar_arrive_expect_tx(bres, (uint32_t)(p.b_stages * B_STAGE_BYTES));
       for (int s = 0; s < p.b_stages; ++s)
         bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), p.b_image + (size_t)s * B_STAGE_BYTES, B_STAGE_BYTES, bres);
-      int it = 0;
-      long long w_empty = 0, t_begin = prof_clock();
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
-        const int py = rem / p.PX, px = rem - py * p.PX;
-        for (int pl = 0; pl < p.n_planes; ++pl, ++it) {
-          const int slot = it % S;
-          const long long t0 = prof_clock();
-          mbar_wait(empty0 + 8 * slot, ((it / S) & 1) ^ 1);
-          w_empty += prof_clock() - t0;
+    }
+    __syncwarp();
+    int slot = 0;
+    uint32_t par = 1;
+    const int step_img = (int)gridDim.x / tiles_per_img, step_rem = (int)gridDim.x - step_img * tiles_per_img;
+    int img = (int)blockIdx.x / tiles_per_img, rem = (int)blockIdx.x - img * tiles_per_img;
+    long long w_empty = 0, t_begin = prof_clock();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int py = rem / p.PX, px = rem - py * p.PX;
+      for (int pl = 0; pl < p.n_planes; ++pl) {
+        const long long t0 = prof_clock();
+        mbar_wait(empty0 + 8 * slot, par);
+        w_empty += prof_clock() - t0;
+        if (leader) {
           mbar_arrive_expect_tx(full0 + 8 * slot, (uint32_t)(p.plane_rows[pl] * p.BW * 128));
           tma_load_4d(smem_u32(sA + (size_t)slot * p.slot_bytes), &tmap, p.plane_chunk[pl] * 64, px * p.BW,
                       p.stride * (py * p.BR) + p.plane_rho[pl], img, full0 + 8 * slot);
         }
+        __syncwarp();
+        if (++slot == S) { slot = 0; par ^= 1u; }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = w_empty; p.dbg[blockIdx.x * 8 + 1] = prof_clock() - t_begin; }
+      rem += step_rem; img += step_img;
+      if (rem >= tiles_per_img) { rem -= tiles_per_img; ++img; }
     }
+    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = w_empty; p.dbg[blockIdx.x * 8 + 1] = prof_clock() - t_begin; }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
@@ -210,22 +226,20 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
     tc_fence_before();
   } else {
     // ===================== epilogue (warps 2..17) =====================
-    // TMEM -> registers -> (LeakyReLU on packed bf16x2) -> global: each thread owns 32 contiguous bytes of one
-    // output pixel-group row; no shared-memory staging, no block barriers.
-    const int r = q * 32 + lane, rr = r >> 3, w = r & 7;  // BW = 8
-    const long long thr_off = p.out_origin_b + (long long)rr * p.out_pitch_y_b + (long long)w * p.out_col_step_b +
-                              cg * COLS * 2;
+    // TMEM -> registers -> (LeakyReLU on packed bf16x2) -> per-quadrant staging -> coalesced global stores.
+    // TMEM lane r = q*32 + lane is pixel group (patch row r / 8, column r % 8): BW = 8, N = 64 -> 128 B per group.
     const int step_img = (int)gridDim.x / tiles_per_img, step_rem = (int)gridDim.x - step_img * tiles_per_img;
     int img = (int)blockIdx.x / tiles_per_img, rem = (int)blockIdx.x - img * tiles_per_img;
     const uint32_t mpx = (uint32_t)((65536 + p.PX - 1) / p.PX);                 // rem < 65536 / PX
     int tcount = 0;
-    long long w_tfull = 0, t_begin = prof_clock();
+    long long w_tfull = 0, w_tmem = 0, t_begin = prof_clock();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int ab = tcount & 1;
       const int py = (int)(((uint32_t)rem * mpx) >> 16), px = rem - py * p.PX;
       const long long t0 = prof_clock();
       mbar_wait(tfull0 + 8 * ab, (tcount >> 1) & 1);
-      w_tfull += prof_clock() - t0;
+      const long long t1 = prof_clock();
+      w_tfull += t1 - t0;
       tc_fence_after();
       uint32_t acc[COLS];
       tmem_ld16(t_lane + (uint32_t)(ab * BN), acc);
@@ -235,23 +249,38 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * ab);       // this warp's slice is in registers and re-armed
+      const long long t2 = prof_clock();
+      w_tmem += t2 - t1;
       uint32_t packed[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e)
         packed[e] = p.act ? pack_lrelu_bf16x2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]))
                           : pack_bf16x2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
-      const int oy = py * p.BR + rr, oxb = px * p.BW + w;
-      if (rr < p.BR && oy < p.Ho && oxb < p.Wox) {
-        uint8_t* o = p.out + (thr_off + (long long)img * p.out_pitch_n_b + (long long)(py * p.BR) * p.out_pitch_y_b +
-                              (long long)(px * p.BW) * p.out_col_step_b);
-        st_global_v4(o, packed[0], packed[1], packed[2], packed[3]);
-        st_global_v4(o + 16, packed[4], packed[5], packed[6], packed[7]);
+      // Stage the quadrant's 32 rows x 128 B (four warps, 32 B per lane each), then every warp writes ONE patch row of
+      // the quadrant — 8 pixel groups x 128 B = 1 KB contiguous in global memory — with two fully coalesced 512-byte
+      // stores.  (Storing each lane's 32 bytes directly costs 32 line requests per instruction: the kernel was bound
+      // by exactly that, 1800 of 2000 cycles per tile in the store phase.)  Two buffers: the barrier of tile t+1
+      // orders the copy-out of tile t before the staging writes of tile t+2.
+      const uint32_t sbuf = stage_s + (uint32_t)(((tcount & 1) * 4 + q) * (32 * EPI_ROW));
+      st_shared_v4(sbuf + (uint32_t)(lane * EPI_ROW + cg * 32), packed[0], packed[1], packed[2], packed[3]);
+      st_shared_v4(sbuf + (uint32_t)(lane * EPI_ROW + cg * 32 + 16), packed[4], packed[5], packed[6], packed[7]);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+      const int prow = 4 * q + cg, oy = py * p.BR + prow;             // this warp's patch row
+      if (prow < p.BR && oy < p.Ho) {
+        uint8_t* orow = p.out + (p.out_origin_b + (long long)img * p.out_pitch_n_b + (long long)oy * p.out_pitch_y_b +
+                                 (long long)(px * p.BW) * p.out_col_step_b);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int g = (lane >> 3) + 4 * k, c = lane & 7;
+          const uint4 v = ld_shared_v4(sbuf + (uint32_t)((cg * 8 + g) * EPI_ROW + c * 16));
+          if (px * p.BW + g < p.Wox) st_global_v4(orow + g * 128 + c * 16, v.x, v.y, v.z, v.w);
+        }
       }
       rem += step_rem; img += step_img;
       if (rem >= tiles_per_img) { rem -= tiles_per_img; ++img; }
     }
     if (p.dbg && warp == 2 && lane == 0) {
-      p.dbg[blockIdx.x * 8 + 5] = w_tfull; p.dbg[blockIdx.x * 8 + 6] = prof_clock() - t_begin;
+      p.dbg[blockIdx.x * 8 + 5] = w_tfull; p.dbg[blockIdx.x * 8 + 6] = prof_clock() - t_begin; p.dbg[blockIdx.x * 8 + 7] = w_tmem;
     }
   }
   __syncthreads();
@@ -264,7 +293,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_bf16_kernel(const __gr
 
 template <int BN>
 size_t tma_smem_bytes(int n_slots, int slot_bytes, int b_stages) {
-  return 1024 + (size_t)n_slots * slot_bytes + (size_t)b_stages * BN * 128 + 256 * 4 + (2 * MAX_SLOTS + 8) * 8 + 16 * 4;
+  return 1024 + (size_t)n_slots * slot_bytes + (size_t)b_stages * BN * 128 + 256 * 4 + (2 * MAX_SLOTS + 8) * 8 + 16 * 4 +
+         EPI_STAGE_BYTES;
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -466,8 +496,8 @@ cudaError_t launch_conv_tma(const TmaPlan& plan, const float* bias, void* out, c
     cudaMemcpy(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
     double a[8] = {0};
     for (int i = 0; i < grid; ++i) for (int j = 0; j < 8; ++j) a[j] += (double)h[i * 8 + j] / grid;
-    fprintf(stderr, "[uahn-tma] Cin=%d Cout=%d out=%dx%d tiles/CTA=%.1f planes=%d | producer: wait_empty %.0f of %.0f | mma: wait_tempty %.0f wait_full %.0f of %.0f | epi(w2): wait_tfull %.0f of %.0f  (cycles, mean over CTAs)\n",
-            g.Cin, g.Cout, g.Ho, g.Wo, (double)tiles / grid, p.n_planes, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+    fprintf(stderr, "[uahn-tma] Cin=%d Cout=%d out=%dx%d tiles/CTA=%.1f planes=%d | producer: wait_empty %.0f of %.0f | mma: wait_tempty %.0f wait_full %.0f of %.0f | epi(w2): wait_tfull %.0f tmem ld/st+arrive %.0f of %.0f  (cycles, mean over CTAs)\n",
+            g.Cin, g.Cout, g.Ho, g.Wo, (double)tiles / grid, p.n_planes, a[0], a[1], a[2], a[3], a[4], a[5], a[7], a[6]);
   }
   return cudaSuccess;
 }
