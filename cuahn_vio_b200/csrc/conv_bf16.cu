@@ -61,6 +61,8 @@ struct IgemmParams {
   unsigned long long* dbg;  // optional [grid][16] cycle counters (UAHN_IG_PROFILE)
 };
 constexpr int AM_GATHER = 0, AM_MC = 1, AM_IM2COL = 2;
+// the MC-dropout producer gets four more warps (10-13): two warps share a stage, four stages are under construction
+constexpr int ig_threads(int am) { return am == AM_MC ? IG_THREADS + 128 : IG_THREADS; }
 
 // -DUAHN_IG_PROFILE=1 + UAHN_IG_DEBUG=1: per-role cycle counters of the im2col-mode kernels (printed per launch)
 #ifndef UAHN_IG_PROFILE
@@ -94,7 +96,7 @@ constexpr int stage_row_bytes() { return epi_chunk<BN>() * 2 + 16; }   // stagin
 // complete on the leader's full barrier; the leader's tcgen05.commit multicasts to the empty / accumulator-full
 // barriers of both CTAs; the peer's epilogue warps release the accumulator on the leader's barrier.
 template <int BN, int STAGES, bool B_RES, int AM = AM_GATHER, bool PAIR = false>
-__global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __grid_constant__ IgemmParams p,
+__global__ void __launch_bounds__(ig_threads(AM), 1) conv_igemm_bf16_kernel(const __grid_constant__ IgemmParams p,
                                                                          const __grid_constant__ CUtensorMap amap,
                                                                          const __grid_constant__ CUtensorMap bmap) {
   static_assert(!PAIR || (AM != AM_GATHER && !B_RES), "CTA pairs: im2col or MC producer, streamed B");
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
       for (int s = 0; s < STAGES; ++s) {
         // im2col: one arrive.expect_tx for A and B together; MC: the stage's producer warp (of each CTA) + the B
         // loader's expect_tx; gather: 128 producer threads (+ the B loader)
-        mbar_init(full0 + 8 * s, AM == AM_IM2COL ? 1 : MC_A ? NCTA + 1 : (B_RES ? 128 : 129));
+        mbar_init(full0 + 8 * s, AM == AM_IM2COL ? 1 : MC_A ? 2 * NCTA + 1 : (B_RES ? 128 : 129));
         mbar_init(empty0 + 8 * s, 1);                  // one tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
-  for (int i = tid; i < p.n_total; i += IG_THREADS) sBias[i] = p.bias_x[i];
+  for (int i = tid; i < p.n_total; i += ig_threads(AM)) sBias[i] = p.bias_x[i];
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
@@ -227,39 +229,39 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
         }
       }
     }
-  } else if (MC_A && warp < 4) {
+  } else if (MC_A && (warp < 4 || warp >= 10)) {
     // ===================== masked-feature producer (MC-dropout GEMM) =====================
-    // Producer warp w builds every 4th stage (global stage counter it = w mod 4) on its own, so four stages are under
-    // construction at once: the per-stage chain wait(empty) -> stores -> fence.proxy.async -> arrive is latency-, not
-    // issue-bound, and four warps working on the SAME stage ran it once per ~800 cycles.
-    // lane -> (granule j of the stage, pair group pg); the lane handles pairs pg and pg + 4 of the tile's 8, all 16 samples.
-    const int j = lane & 7, pg = lane >> 3;
+    // Producer warps w and w + 10 build every 4th stage (global stage counter it = w mod 4) between them, so four
+    // stages are under construction at once: the per-stage chain wait(empty) -> stores -> fence.proxy.async -> arrive
+    // is latency-, not issue-bound, and four warps working on the SAME stage ran it once per ~800 cycles.
+    // lane -> (granule j of the stage, pair pg + 4 * hw of the tile's 8), all 16 samples: 16 stores per stage.
+    const int j = lane & 7, pg = (lane >> 3) + (warp < 4 ? 0 : 4), pwarp = warp < 4 ? warp : warp - 10;
     const int my_tiles = total_tiles > cid ? (total_tiles - cid + ncl - 1) / ncl : 0;
     const int n_it = my_tiles * p.k_stages;
     long long pw = 0;
     const long long pbeg = ig_clock();
     auto src = [&](int it, int pp, const uint8_t*& f, const uint8_t*& mb) -> bool {
       const int tl = it / p.k_stages, st = it - tl * p.k_stages;
-      const int pair = (tile_m0(cid + tl * ncl) >> 4) + pg + 4 * pp;
+      const int pair = (tile_m0(cid + tl * ncl) >> 4) + pg;
       f = p.in + (size_t)pair * (FC_IN * 2) + (size_t)st * 128 + j * 16;
       mb = p.mc_bits + ((size_t)pair * (FC_IN / 8) + (size_t)st * 8 + j) * MC;
       return pair * MC < p.M_rows;
     };
-    uint4 gq[2], mq[2];                                   // this warp's next stage, fetched one round (4 stages) ahead
+    uint4 gq[1], mq[1];                                   // this warp's next stage, fetched one round (4 stages) ahead
 #pragma unroll
-    for (int pp = 0; pp < 2; ++pp) {
+    for (int pp = 0; pp < 1; ++pp) {
       gq[pp] = mq[pp] = make_uint4(0u, 0u, 0u, 0u);
       const uint8_t *f, *mb;
-      if (warp < n_it && src(warp, pp, f, mb)) {
+      if (pwarp < n_it && src(pwarp, pp, f, mb)) {
         gq[pp] = __ldg(reinterpret_cast<const uint4*>(f));
         mq[pp] = __ldg(reinterpret_cast<const uint4*>(mb));
       }
     }
-    for (int it = warp; it < n_it; it += 4) {
+    for (int it = pwarp; it < n_it; it += 4) {
       const int slot = it % STAGES;
-      uint4 g[2] = {gq[0], gq[1]}, mk[2] = {mq[0], mq[1]};
+      uint4 g[1] = {gq[0]}, mk[1] = {mq[0]};
 #pragma unroll
-      for (int pp = 0; pp < 2; ++pp) {
+      for (int pp = 0; pp < 1; ++pp) {
         gq[pp] = mq[pp] = make_uint4(0u, 0u, 0u, 0u);
         const uint8_t *f, *mb;
         if (it + 4 < n_it && src(it + 4, pp, f, mb)) {
@@ -268,9 +270,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
         }
       }
       // kept values are scaled by 1/0.95 in fp32 and rounded to bf16 once per pair (same rounding as mc_expand)
-      uint32_t sc[2][4];
+      uint32_t sc[1][4];
 #pragma unroll
-      for (int pp = 0; pp < 2; ++pp) {
+      for (int pp = 0; pp < 1; ++pp) {
         const uint32_t w[4] = {g[pp].x, g[pp].y, g[pp].z, g[pp].w};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
       pw += ig_clock() - t0;
       const uint32_t stage = smem_u32(sA + slot * A_STAGE_BYTES);
 #pragma unroll
-      for (int pp = 0; pp < 2; ++pp) {
+      for (int pp = 0; pp < 1; ++pp) {
         const uint32_t mw[4] = {mk[pp].x, mk[pp].y, mk[pp].z, mk[pp].w};
 #pragma unroll
         for (int si = 0; si < MC; ++si) {
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_bf16_kernel(const __
             const uint32_t b2 = bits >> (2 * c);
             o[c] = sc[pp][c] & (((b2 & 1u) ? 0x0000FFFFu : 0u) | ((b2 & 2u) ? 0xFFFF0000u : 0u));
           }
-          const int r = (pg + 4 * pp) * MC + si;
+          const int r = pg * MC + si;
           st_shared_v4(stage + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)), o[0], o[1], o[2], o[3]);
         }
       }
@@ -562,7 +564,7 @@ cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st, const C
   const int units = ((p.m_tiles + NCTA - 1) / NCTA) * p.n_tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(NCTA * std::min(units, num_sms / NCTA));
-  cfg.blockDim = dim3(IG_THREADS);
+  cfg.blockDim = dim3(ig_threads(AM));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[2];
