@@ -83,7 +83,7 @@ __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : v * LRELU
 
 // ---- Philox4x32-7 (host + device): the in-kernel MC-dropout mask source ---------------------------------
 // 7 rounds is the smallest Crush-resistant Philox4x32 (Salmon et al., SC'11; 10 is the library default's safety
-// margin).  The masks cost 20 480 Philox blocks per pair, so the rounds are the run time of mc_maskbits_kernel.
+// margin).  The masks cost 5 120 Philox blocks per pair and head.
 constexpr int PHILOX_ROUNDS = 7;
 struct Philox {
   static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -107,21 +107,62 @@ struct Philox {
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
   }
 };
-// A unit is dropped iff its 16-bit draw < DROP_THRESH_16  (p = 3277/65536 = 0.0500031).
-constexpr uint32_t DROP_THRESH_16 = 3277u;
-// keep decision for (pair, head, layer, sample, index): one Philox block serves 8 consecutive indices.
-__host__ __device__ inline uint32_t philox_keep8(uint64_t seed, uint64_t pair, int head, int layer, int sample,
-                                                 int idx8) {
-  uint32_t r[4];
-  Philox::gen(seed, (uint32_t)idx8, (uint32_t)(sample | (head << 8) | (layer << 16)), (uint32_t)pair,
-              (uint32_t)(pair >> 32), r);
-  uint32_t bits = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    bits |= ((r[i] & 0xFFFFu) >= DROP_THRESH_16 ? 1u : 0u) << (2 * i);
-    bits |= ((r[i] >> 16) >= DROP_THRESH_16 ? 1u : 0u) << (2 * i + 1);
+// The keep byte of 8 consecutive units comes from ONE 32-bit uniform through a Walker/Vose alias table over the 256
+// byte patterns: P(byte = b) = 19^popcount(b) / 20^8, i.e. every unit is kept independently with probability 0.95
+// (nn.Dropout(p = 0.05)), exact up to the 24-bit column threshold.  One Philox block therefore serves 32 units instead
+// of 8 (the rounds are the run time of mc_maskbits_kernel) and the decode is branch-free: no per-unit compare.
+//   tab[c] = threshold(24 bits) << 8 | alias(8 bits);  byte = (u & 0xFFFFFF) < threshold ? c : alias,  c = u >> 24.
+__host__ __device__ inline uint32_t alias_keep_byte(uint32_t u, const uint32_t* tab) {
+  const uint32_t c = u >> 24, e = tab[c];
+  return (u & 0xFFFFFFu) < (e >> 8) ? c : (e & 0xFFu);
+}
+// Exact integer construction (Vose): pattern weights 256 * 19^popcount against a column capacity of 20^8, so the table
+// is the same on every host that builds it.
+inline void build_keep_alias_table(uint32_t tab[256]) {
+  const unsigned long long W = 25600000000ull;            // 20^8
+  unsigned long long pow19[9], w[256];
+  pow19[0] = 1;
+  for (int i = 1; i <= 8; ++i) pow19[i] = pow19[i - 1] * 19ull;
+  int small[256], large[256], ns = 0, nl = 0;
+  unsigned long long thr[256];
+  int alias[256];
+  for (int b = 0; b < 256; ++b) {
+    int pop = 0;
+    for (int j = 0; j < 8; ++j) pop += (b >> j) & 1;
+    w[b] = 256ull * pow19[pop];
+    thr[b] = W;
+    alias[b] = b;
+    if (w[b] < W) small[ns++] = b; else large[nl++] = b;
   }
-  return bits;  // bit j = keep(index idx8*8 + j)
+  while (ns > 0 && nl > 0) {
+    const int l = small[--ns], g = large[--nl];
+    thr[l] = w[l];
+    alias[l] = g;
+    w[g] = w[g] + w[l] - W;
+    if (w[g] < W) small[ns++] = g; else large[nl++] = g;
+  }
+  for (int b = 0; b < 256; ++b) {
+    unsigned long long t24 = thr[b] >= W ? 0xFFFFFFull : (thr[b] << 24) / W;   // floor(thr * 2^24 / 20^8), thr < 2^35
+    tab[b] = (uint32_t)(t24 << 8) | (uint32_t)alias[b];
+  }
+}
+// keep byte for (pair, head, layer, sample, index / 8): Philox block idx8 / 4, word idx8 % 4.  bit j = keep(idx8*8 + j).
+__host__ __device__ inline uint32_t philox_keep8(uint64_t seed, uint64_t pair, int head, int layer, int sample, int idx8,
+                                                 const uint32_t* alias_tab) {
+  uint32_t r[4];
+  Philox::gen(seed, (uint32_t)(idx8 >> 2), (uint32_t)(sample | (head << 8) | (layer << 16)), (uint32_t)pair,
+              (uint32_t)(pair >> 32), r);
+  const uint32_t u = (idx8 & 2) ? ((idx8 & 1) ? r[3] : r[2]) : ((idx8 & 1) ? r[1] : r[0]);
+  return alias_keep_byte(u, alias_tab);
+}
+// the four keep bytes of Philox block idx32 (units idx32*32 ... +31) from one block
+__host__ __device__ inline void philox_keep32(uint64_t seed, uint64_t pair, int head, int layer, int sample, int idx32,
+                                              const uint32_t* alias_tab, uint32_t out[4]) {
+  uint32_t r[4];
+  Philox::gen(seed, (uint32_t)idx32, (uint32_t)(sample | (head << 8) | (layer << 16)), (uint32_t)pair,
+              (uint32_t)(pair >> 32), r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = alias_keep_byte(r[i], alias_tab);
 }
 
 }  // namespace uahn

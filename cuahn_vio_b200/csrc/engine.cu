@@ -580,6 +580,10 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
     }
     h->own_stream = true;
   }
+  if ((e = init_keep_alias_table()) != cudaSuccess) {
+    h->fail(UAHN_ERR_CUDA, "keep-byte alias table upload: %s", cudaGetErrorString(e));
+    return bail(UAHN_ERR_CUDA);
+  }
   std::map<std::string, HostTensor> w;
   std::string err;
   if (!load_weight_file(cfg->weights_path, w, err)) {
@@ -958,18 +962,21 @@ int uahn_profile_read(uahn_handle* h, double* ms4, uint64_t* launches4) {
 
 int uahn_philox_keep_masks(uint64_t seed, uint64_t pair_index, uint8_t* out) {
   if (!out) return UAHN_ERR_INVALID;
+  static uint32_t tab[256];
+  static const bool tab_ready = (build_keep_alias_table(tab), true);
+  (void)tab_ready;
   for (int head = 0; head < 2; ++head)
     for (int s = 0; s < MC; ++s) {
       uint8_t* row = out + ((size_t)head * MC + s) * MASK_ROW;
       for (int k8 = 0; k8 < FC_IN / 8; ++k8) {
-        const uint32_t bits = philox_keep8(seed, pair_index, head, 0, s, k8);
+        const uint32_t bits = philox_keep8(seed, pair_index, head, 0, s, k8, tab);
         for (int j = 0; j < 8; ++j) {
           const int kp = k8 * 8 + j, hw = kp >> 8, c = kp & 255;   // kernel order -> reference order
           row[c * 20 + hw] = (bits >> j) & 1u;
         }
       }
       for (int j8 = 0; j8 < FC_HID / 8; ++j8) {
-        const uint32_t bits = philox_keep8(seed, pair_index, head, 1, s, j8);
+        const uint32_t bits = philox_keep8(seed, pair_index, head, 1, s, j8, tab);
         for (int j = 0; j < 8; ++j) row[FC_IN + j8 * 8 + j] = (bits >> j) & 1u;
       }
     }

@@ -192,6 +192,10 @@ __global__ void __launch_bounds__(256) fc8_dlt_kernel(int n, const T* __restrict
 
 // A'[head][pair][s][k'] = keep ? feat[k'] * (1/0.95) : 0     (Dropout(0.05) on the repeated feature)
 // k' = NHWC index (hw*256 + c); explicit masks are indexed in the reference order kref = c*20 + hw.
+// alias table of the keep-byte generator (common.cuh: alias_keep_byte), uploaded once per device by
+// init_keep_alias_table()
+__device__ uint32_t g_keep_alias[256];
+
 template <typename T>
 __global__ void __launch_bounds__(256) mc_expand_kernel(const T* __restrict__ feat, T* __restrict__ A, int n,
                                                          const uint8_t* __restrict__ keep_masks, uint64_t seed,
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(256) mc_expand_kernel(const T* __restrict__ fe
         bits |= (m[c * 20 + hw] ? 1u : 0u) << j;
       }
     } else {
-      bits = philox_keep8(seed, first_pair + pair, head, 0, s, k8);
+      bits = philox_keep8(seed, first_pair + pair, head, 0, s, k8, g_keep_alias);
     }
     T v[8];
     if constexpr (sizeof(T) == 2) {
@@ -305,22 +309,33 @@ __global__ void __launch_bounds__(256) mc_maskbits_kernel(uint8_t* __restrict__ 
   if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }
   const int pair = blockIdx.x, head = blockIdx.y;
   uint8_t* o = bits_out + ((size_t)head * n + pair) * (FC_IN / 8) * MC;
-#pragma unroll 4      // independent Philox chains per thread: the kernel is the latency of 7 dependent multiply rounds
-  for (int i = threadIdx.x; i < MC * (FC_IN / 8); i += blockDim.x) {
-    const int k8 = i / MC, smp = i - k8 * MC;            // consecutive threads -> consecutive bytes
-    uint32_t bits;
-    if (keep_masks) {
+  if (keep_masks) {
+    for (int i = threadIdx.x; i < MC * (FC_IN / 8); i += blockDim.x) {
+      const int k8 = i / MC, smp = i - k8 * MC;            // consecutive threads -> consecutive bytes
       const uint8_t* m = keep_masks + ((size_t)(pair * 2 + head) * MC + smp) * MASK_ROW;
-      bits = 0;
+      uint32_t bits = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int kp = k8 * 8 + j, hw = kp >> 8, c = kp & 255;   // kernel order -> reference order c*20 + hw
         bits |= (m[c * 20 + hw] ? 1u : 0u) << j;
       }
-    } else {
-      bits = philox_keep8(seed, first_pair + pair, head, 0, smp, k8);
+      o[i] = (uint8_t)bits;
     }
-    o[i] = (uint8_t)bits;
+    return;
+  }
+  // One Philox block -> four keep bytes (32 units) of one sample through the alias table (shared-memory copy: the
+  // look-up index is random).  Thread -> (block k32, sample): its bytes k8 = 4*k32 .. +3 land 16 bytes apart, the 16
+  // samples of a k8 in consecutive bytes.
+  __shared__ uint32_t s_tab[256];
+  s_tab[threadIdx.x] = g_keep_alias[threadIdx.x];
+  __syncthreads();
+#pragma unroll 2      // independent Philox chains per thread: 7 dependent multiply rounds each
+  for (int i = threadIdx.x; i < MC * (FC_IN / 32); i += blockDim.x) {
+    const int k32 = i / MC, smp = i - k32 * MC;
+    uint32_t b[4];
+    philox_keep32(seed, first_pair + pair, head, 0, smp, k32, s_tab, b);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[(k32 * 4 + q) * MC + smp] = (uint8_t)b[q];
   }
 }
 
@@ -368,7 +383,7 @@ __global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid
 #pragma unroll
         for (int j = 0; j < 8; ++j) mybits[jo] |= (m[j8 * 8 + j] ? 1u : 0u) << j;
       } else {
-        mybits[jo] = philox_keep8(seed, first_pair + pair, head, 1, s, j8);
+        mybits[jo] = philox_keep8(seed, first_pair + pair, head, 1, s, j8, g_keep_alias);
       }
     }
     const int lane_base = (tid & 31) & ~7;
@@ -504,6 +519,13 @@ template cudaError_t launch_mc_expand<__nv_bfloat16>(int, const __nv_bfloat16*, 
 cudaError_t launch_mc_fc1_small(int n, const void* A, const void* W, const float* bias, void* out, cudaStream_t st) {
   return launch_pdl(mc_fc1_small_kernel, dim3(FC_HID / FC1S_JT, n), dim3(256), 0, st, (const __nv_bfloat16*)A,
                     (const __nv_bfloat16*)W, bias, (__nv_bfloat16*)out);
+}
+
+// host side: build the alias table and upload it to the current device (idempotent; called by uahn_create)
+cudaError_t init_keep_alias_table() {
+  uint32_t tab[256];
+  build_keep_alias_table(tab);
+  return cudaMemcpyToSymbol(g_keep_alias, tab, sizeof(tab));
 }
 
 cudaError_t launch_mc_maskbits(int n, uint8_t* bits, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,

@@ -48,6 +48,29 @@ def test_philox_masks_host(lib):
     assert set(np.unique(a)) == {0, 1}
 
 
+def test_philox_masks_are_iid_bernoulli():
+    """The keep bytes come from an alias table over the 256 byte patterns (one 32-bit uniform per 8 units): the units must
+    still be independent Bernoulli(0.95) — keep rate, drops per byte ~ Binomial(8, 0.05), uniform drop position."""
+    from math import comb
+    from cuahn_vio_b200 import api
+    m = np.stack([api.philox_keep_masks(11, i) for i in range(20)])[..., :5120]       # first dropout, reference order
+    kp = np.arange(5120)
+    ref = (kp & 255) * 20 + (kp >> 8)                                                  # kernel order -> reference order
+    drop = 1 - m.reshape(-1, 5120)[:, ref].astype(np.float64)                          # [640 rows, 5120] in kernel order
+    n = drop.size
+    assert abs(drop.mean() - 0.05) < 4 * (0.05 * 0.95 / n) ** 0.5
+    per_byte = drop.reshape(-1, 8).sum(1).astype(int)
+    nb = per_byte.size
+    freq = np.bincount(per_byte, minlength=9) / nb
+    for k in range(5):
+        e = comb(8, k) * 0.05 ** k * 0.95 ** (8 - k)
+        assert abs(freq[k] - e) < 5 * (e * (1 - e) / nb) ** 0.5 + 1e-7, (k, freq[k], e)
+    single = drop.reshape(-1, 8)[per_byte == 1].mean(0)
+    assert np.abs(single - 0.125).max() < 0.004
+    has = drop.reshape(drop.shape[0], 640, 8).sum(2) > 0                               # neighbouring bytes independent
+    assert abs((has[:, :-1] & has[:, 1:]).mean() - has.mean() ** 2) < 0.003
+
+
 def test_weight_export_roundtrip(tmp_path, synth_sd):
     from cuahn_vio_b200 import weights, synthetic
     p = str(tmp_path / "w.bin")
