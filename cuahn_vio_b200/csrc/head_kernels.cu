@@ -373,23 +373,24 @@ __global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid
     const T* hrow = hid + (((size_t)head * n + pair) * MC + s) * FC_HID;
     const uint8_t* m = keep_masks ? keep_masks + ((size_t)(pair * 2 + head) * MC + s) * MASK_ROW + FC_IN : nullptr;
     float acc = 0.f;
-    // the 8 lanes of one (head, sample) share the hidden-layer keep bits: lane oo draws blocks oo, oo+8, oo+16, oo+24
+    // the 8 lanes of one (head, sample) share the hidden-layer keep bits: lane oo owns bytes 4*oo .. 4*oo+3, the four
+    // keep bytes of ONE Philox block
     uint32_t mybits[4];
+    if (m) {
 #pragma unroll
-    for (int jo = 0; jo < 4; ++jo) {
-      const int j8 = jo * 8 + oo;
-      if (m) {
+      for (int jo = 0; jo < 4; ++jo) {
+        const int j8 = 4 * oo + jo;
         mybits[jo] = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) mybits[jo] |= (m[j8 * 8 + j] ? 1u : 0u) << j;
-      } else {
-        mybits[jo] = philox_keep8(seed, first_pair + pair, head, 1, s, j8, g_keep_alias);
       }
+    } else {
+      philox_keep32(seed, first_pair + pair, head, 1, s, oo, g_keep_alias, mybits);
     }
     const int lane_base = (tid & 31) & ~7;
 #pragma unroll
     for (int j8 = 0; j8 < FC_HID / 8; ++j8) {
-      const uint32_t bits = __shfl_sync(0xffffffffu, mybits[j8 >> 3], lane_base | (j8 & 7));
+      const uint32_t bits = __shfl_sync(0xffffffffu, mybits[j8 & 3], lane_base | (j8 >> 2));
       T hv[8];
       if constexpr (sizeof(T) == 2) {
         *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(hrow + j8 * 8);
