@@ -12,7 +12,7 @@ import numpy as np
 
 IMG_H, IMG_W = 224, 320
 MASK_BYTES_PER_PAIR = 2 * 16 * (5120 + 256)
-VARIANTS = {"full": 0, "prior3": 1, "prior2": 2, "prior1": 3}
+VARIANTS = {"auto": -1, "full": 0, "prior3": 1, "prior2": 2, "prior1": 3}
 PRECISIONS = {"fp32": 0, "bf16": 1}
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libuahn.so")
 EXPORTED_SYMBOLS = [
@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "uahn_infer_batch_device", "uahn_synchronize", "uahn_stream", "uahn_launch_count",
     "uahn_latest_inference_time", "uahn_image_count", "uahn_philox_keep_masks", "uahn_stage_dlt",
     "uahn_stage_warp", "uahn_debug_read", "uahn_profile_enable", "uahn_profile_read", "uahn_stage_conv", "uahn_submit_batch", "uahn_submit_sequence",
-    "uahn_wait",
+    "uahn_wait", "uahn_stage_transfer", "uahn_variant", "uahn_show_error",
 ]
 PREPROC_SYMBOLS = ["uahn_undistort_init_maps", "uahn_set_undistort_maps", "uahn_load_raw_image", "uahn_stage_undistort"]
 EKF_SYMBOLS = ["uahn_ekf_prior_px", "uahn_ekf_update", "uahn_ekf_reset_offsets", "uahn_ekf_iekf_frame",
@@ -164,6 +164,12 @@ def load_library(path: str | None = None):
     lib.uahn_stage_dlt.restype = i
     lib.uahn_stage_warp.argtypes = [vp, i, vp, vp, vp, vp, vp]
     lib.uahn_stage_warp.restype = i
+    lib.uahn_stage_transfer.argtypes = [vp, i, vp, vp, vp, vp, vp]
+    lib.uahn_stage_transfer.restype = i
+    lib.uahn_variant.argtypes = [vp]
+    lib.uahn_variant.restype = i
+    lib.uahn_show_error.argtypes = [vp]
+    lib.uahn_show_error.restype = i
     lib.uahn_profile_enable.argtypes = [vp, i]
     lib.uahn_profile_enable.restype = i
     lib.uahn_profile_read.argtypes = [vp, vp, vp]
@@ -258,13 +264,16 @@ class Uahn:
         self._lib = load_library()
         self._h = C.c_void_p()
         self.variant, self.show_error, self.precision, self.max_batch = variant, show_error, precision, max_batch
-        cfg = _Config(os.fsencode(weights_path), VARIANTS[variant], int(show_error), PRECISIONS[precision], device,
-                      max_batch, stream)
+        cfg = _Config(os.fsencode(weights_path), VARIANTS[variant], -1 if show_error is None else int(show_error),
+                      PRECISIONS[precision], device, max_batch, stream)
         rc = self._lib.uahn_create(C.byref(cfg), C.byref(self._h))
         if rc:
             msg = self._lib.uahn_last_error(None).decode()
             self._h = None
             raise UahnError(f"uahn_create failed ({rc}): {msg}")
+        # "auto" / None: resolved from the records weights.export_torchscript wrote into the file
+        self.variant = {v: k for k, v in VARIANTS.items()}[self._lib.uahn_variant(self._h)]
+        self.show_error = bool(self._lib.uahn_show_error(self._h))
 
     def close(self):
         h = getattr(self, "_h", None)
@@ -308,13 +317,19 @@ class Uahn:
         self._check(self._lib.uahn_stage_undistort(self._h, _ptr(raw), raw.shape[0], raw.shape[1], raw.strides[0], _ptr(out)))
         return out
 
-    def infer(self, prior_px=None, seed: int = 0, pair_index: int = 0, keep_masks: np.ndarray | None = None,
+    def infer(self, prior_px=None, seed: int = 0, pair_index: int | None = None, keep_masks: np.ndarray | None = None,
               want_error: bool = False):
+        """pair_index None (default): the handle numbers its calls itself, so every forward draws fresh MC-dropout
+        masks like the reference (model_to_trace.py:266-273); an explicit (seed, pair_index) replays a given draw."""
         prior = None if prior_px is None else np.ascontiguousarray(prior_px, np.float64).reshape(8)
         mean, cov = np.empty(8, np.float64), np.empty((8, 8), np.float64)
         err = np.empty((IMG_H, IMG_W), np.uint8) if want_error else None
-        rng = self._rng(seed, pair_index, keep_masks)
-        self._check(self._lib.uahn_infer(self._h, _ptr(prior), C.byref(rng), _ptr(mean), _ptr(cov), _ptr(err)))
+        if pair_index is None and keep_masks is None and seed == 0:
+            rng_ref = None
+        else:
+            rng = self._rng(seed, pair_index or 0, keep_masks)
+            rng_ref = C.byref(rng)
+        self._check(self._lib.uahn_infer(self._h, _ptr(prior), rng_ref, _ptr(mean), _ptr(cov), _ptr(err)))
         return mean, cov, err
 
     def infer_batch(self, prev: np.ndarray, curr: np.ndarray, prior: np.ndarray | None = None, seed: int = 0,
@@ -351,12 +366,14 @@ class Uahn:
                                                    _ptr(cov)))
 
     def iekf_frame(self, state: "EkfState", max_iter: int = 1, K_net_Cov: float = 10.0, min_images: int = 10,
-                   use_measurement: bool = True, seed: int = 0, pair_index: int = 0, iterative: "Uahn | None" = None):
-        """One camera frame of the IEKF loop (VioManager.cpp:227-275); returns the last network (mean, cov) in px."""
+                   use_measurement: bool = True, seed: int = 0, pair_index: int | None = None,
+                   iterative: "Uahn | None" = None):
+        """One camera frame of the IEKF loop (VioManager.cpp:227-275); returns the last network (mean, cov) in px.
+        pair_index None: fresh masks on every forward (per-handle counters); explicit: iteration `it` uses pair_index + it."""
         mean, cov = np.empty(8, np.float64), np.empty((8, 8), np.float64)
-        rng = _Rng(seed, pair_index, None)
+        rng = None if pair_index is None and seed == 0 else C.byref(_Rng(seed, pair_index or 0, None))
         self._check(self._lib.uahn_ekf_iekf_frame(self._h, iterative._h if iterative else None, C.byref(state), max_iter,
-                                                  float(K_net_Cov), min_images, int(use_measurement), C.byref(rng),
+                                                  float(K_net_Cov), min_images, int(use_measurement), rng,
                                                   _ptr(mean), _ptr(cov)))
         return mean, cov
 
@@ -407,6 +424,16 @@ class Uahn:
         self._check(self._lib.uahn_stage_warp(self._h, n, _ptr(img), _ptr(H), _ptr(out), _ptr(ix), _ptr(iy)))
         return out, ix, iy
 
+    def stage_transfer(self, var: np.ndarray, Hp: np.ndarray, pts_w: np.ndarray):
+        """transfer_mean_var_single + packing (model_to_trace.py:18-38, 311-317) → flow [n, 8], cov [n, 8, 8]."""
+        var = np.ascontiguousarray(var, np.float32).reshape(-1, 8)
+        n = var.shape[0]
+        Hp = np.ascontiguousarray(Hp, np.float32).reshape(n, 9)
+        pts_w = np.ascontiguousarray(pts_w, np.float32).reshape(n, 8)
+        flow, cov = np.empty((n, 8), np.float32), np.empty((n, 8, 8), np.float32)
+        self._check(self._lib.uahn_stage_transfer(self._h, n, _ptr(var), _ptr(Hp), _ptr(pts_w), _ptr(flow), _ptr(cov)))
+        return flow, cov
+
     def stage_conv(self, layer: str, x: np.ndarray, out_shape) -> np.ndarray:
         """Run one Conv2d+LeakyReLU layer (x: n x Cin x H x W float32) → n x Cout x Ho x Wo."""
         x = np.ascontiguousarray(x, np.float32)
@@ -432,15 +459,23 @@ class HomographyNet:
 
     def __init__(self, network_model_path: str, network_model_iterative_path: str = "", use_prior: bool = True,
                  num_of_iteration: int = 1, show_imgs: bool = False, precision: str = "bf16", device: int = 0,
-                 iterative_variant: str = "prior2"):
+                 iterative_variant: str = "auto"):
         self.use_prior = use_prior
         self.show_error = "_showError" in network_model_path
         self.show_imgs = show_imgs
         self._main = Uahn(network_model_path, "prior3" if use_prior else "full", self.show_error, precision, device, 1)
         self._iter = None
         if num_of_iteration > 1:
-            self._iter = Uahn(network_model_iterative_path or network_model_path, iterative_variant,
-                              "_showError" in (network_model_iterative_path or network_model_path), precision, device, 1)
+            # the reference's second slot runs whatever graph the file holds (HomographyNet.cpp:104-124): "auto" takes the
+            # variant weights.export_torchscript recorded; files without a record fall back to the 2-block schedule
+            ipath = network_model_iterative_path or network_model_path
+            ishow = "_showError" in ipath
+            try:
+                self._iter = Uahn(ipath, iterative_variant, ishow, precision, device, 1)
+            except UahnError:
+                if iterative_variant != "auto":
+                    raise
+                self._iter = Uahn(ipath, "prior2", ishow, precision, device, 1)
         self._mean = np.zeros(8)
         self._cov = np.zeros((8, 8))
         self.error_map = None

@@ -3,6 +3,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef __CUDACC__
+#include <atomic>
+#endif
 
 namespace uahn {
 
@@ -55,6 +58,41 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 #ifdef __CUDACC__
+// ---- per-device host-side caches ----------------------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize and the SM count belong to a DEVICE, and one process may hold handles on
+// several GPUs (uahn_config.device), so the caches are indexed by the current device.  Plain relaxed atomics: a racing
+// second cudaFuncSetAttribute / attribute query is harmless.
+constexpr int UAHN_MAX_DEVICES = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < UAHN_MAX_DEVICES) ? d : 0;
+}
+inline int device_num_sms() {
+  static std::atomic<int> sms[UAHN_MAX_DEVICES];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int v = (dev >= 0 && dev < UAHN_MAX_DEVICES) ? sms[dev].load(std::memory_order_relaxed) : 0;
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < UAHN_MAX_DEVICES) sms[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+struct SmemOptIn {   // one (function-local static) per kernel instantiation
+  std::atomic<size_t> bytes[UAHN_MAX_DEVICES];
+  template <typename K>
+  cudaError_t ensure(K kern, size_t smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool cached = dev >= 0 && dev < UAHN_MAX_DEVICES;
+    if (cached && smem <= bytes[dev].load(std::memory_order_relaxed)) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && cached) bytes[dev].store(smem, std::memory_order_relaxed);
+    return e;
+  }
+};
+
 bool pdl_enabled();   // engine.cu: switched per forward() call by the batch size
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

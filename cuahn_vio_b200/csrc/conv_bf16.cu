@@ -542,12 +542,8 @@ cudaError_t launch_t(const IgemmParams& p, int num_sms, cudaStream_t st, const C
       fixed_smem<BN>() + (size_t)STAGES * A_STAGE_BYTES + (size_t)(B_RES ? p.k_stages : STAGES) * (BN * 128 / NCTA);
   if (smem > SMEM_LIMIT) return cudaErrorInvalidConfiguration;
   auto kern = conv_igemm_bf16_kernel<BN, STAGES, B_RES, AM, PAIR>;
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr = smem;
-  }
+  static SmemOptIn optin;   // per device (common.cuh)
+  if (cudaError_t e = optin.ensure(kern, smem); e != cudaSuccess) return e;
   static const CUtensorMap no_map{};
   if (PAIR && (!bmap || (AM == AM_IM2COL && !amap))) return cudaErrorInvalidValue;
 #if UAHN_IG_PROFILE
@@ -748,12 +744,7 @@ int conv_bf16_prepare(ConvBf16Weights& wb, const std::vector<float>& wk, const s
 cudaError_t launch_mc_gemm_bf16(const ConvBf16Weights& wb, const void* feat, const uint8_t* mc_bits, void* out, int n,
                                 cudaStream_t st) {
   if (!wb.ready || wb.n_total != FC_HID || wb.k_total != FC_IN) return cudaErrorInvalidValue;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int num_sms = device_num_sms();
   IgemmParams p{};
   p.in = (const uint8_t*)feat;
   p.b_image = (const uint8_t*)wb.b_image;
@@ -781,12 +772,7 @@ cudaError_t launch_mc_gemm_bf16(const ConvBf16Weights& wb, const void* feat, con
 cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const float* bias, void* out,
                              const ConvGeom& g, cudaStream_t st) {
   if (!wb.ready) return cudaErrorInvalidValue;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int num_sms = device_num_sms();
   if (wb.tma.enabled) return launch_conv_tma(wb.tma, bias, out, g, num_sms, st);
   IgemmParams p{};
   const int xb = wb.xb;

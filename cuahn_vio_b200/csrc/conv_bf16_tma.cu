@@ -475,12 +475,8 @@ cudaError_t launch_conv_tma(const TmaPlan& plan, const float* bias, void* out, c
 #define UAHN_TMA_CASE(KH_, ST_, CH_, K0_, K1_)                                                                     \
   if (g.KH == KH_ && g.stride == ST_ && plan.chunks == CH_ && ks0 == K0_ && ks1 == K1_) {                          \
     auto kern = conv_tma_bf16_kernel<64, KH_, ST_, CH_, K0_, K1_>;                                                 \
-    static size_t attr = 0;                                                                                         \
-    if (smem > attr) {                                                                                              \
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-      if (e != cudaSuccess) return e;                                                                               \
-      attr = smem;                                                                                                  \
-    }                                                                                                               \
+    static SmemOptIn optin;                                                                                         \
+    if (cudaError_t e = optin.ensure(kern, smem); e != cudaSuccess) return e;                                       \
     lerr = launch_pdl(kern, dim3(grid), dim3(TM_THREADS), smem, st, *tm, p);                                        \
   }
   UAHN_TMA_CASE(7, 1, 1, 2, 0)   // block_4_0 / block_3_0 : 7x7 s1, Cin 2

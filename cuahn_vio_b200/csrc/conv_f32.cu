@@ -98,13 +98,9 @@ template <int BM, int BN, int TM, int TN>
 cudaError_t launch_cfg(const float* in, const float* wk, const float* bias, float* out, const ConvGeom& g,
                        cudaStream_t st) {
   const size_t smem = (size_t)(BK * BM + BK * BN) * 4 + (size_t)BM * 8 + (size_t)g.K * 4;
-  static size_t max_set = 0;
-  if (smem > 48 * 1024 && smem > max_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_f32_kernel<BM, BN, TM, TN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    max_set = smem;
-  }
+  static SmemOptIn optin;   // per device (common.cuh)
+  if (smem > 48 * 1024)
+    if (cudaError_t e = optin.ensure(conv_f32_kernel<BM, BN, TM, TN>, smem); e != cudaSuccess) return e;
   dim3 grid((g.M + BM - 1) / BM, (g.Cout + BN - 1) / BN);
   conv_f32_kernel<BM, BN, TM, TN><<<grid, CONV_THREADS, smem, st>>>(in, wk, bias, out, g);
   return cudaGetLastError();

@@ -138,7 +138,12 @@ int uahn_ekf_iekf_frame(uahn_handle* h, uahn_handle* h_iter, uahn_ekf_state* s, 
     double prior_px[8], propagated[8];
     uahn_ekf_prior_px(s, prior_px, propagated);                                                    // :230-234
     uahn_handle* net = (it > 0 && h_iter) ? h_iter : h;                                            // HomographyNet.cpp:209
-    int rc = uahn_infer(net, prior_px, rng, mean, cov, nullptr);                                   // :236
+    // fresh MC-dropout masks for every forward (model_to_trace.py:266-273): iteration `it` of this frame uses pair index
+    // first_pair_index + it (the caller advances first_pair_index by max_iter per frame); a NULL rng lets each handle
+    // number its own calls
+    uahn_rng it_rng{};
+    if (rng) { it_rng = *rng; it_rng.first_pair_index += (uint64_t)it; }
+    int rc = uahn_infer(net, prior_px, rng ? &it_rng : nullptr, mean, cov, nullptr);               // :236
     if (rc == UAHN_ERR_STATE) continue;        // "Only has one image": outputs untouched, loop goes on (HomographyNet.cpp:155-158)
     if (rc) return rc;
     if (use_measurement && uahn_image_count(h) > min_images) {                                     // :257

@@ -44,31 +44,42 @@ struct HostTensor {
   }
 };
 
+// A truncated or corrupt file must come back as UAHN_ERR_WEIGHTS, never as an exception across the C ABI: every dim is
+// bounded, the payload is checked against the bytes left in the file before anything is allocated, and the caller wraps
+// the whole load in try/catch.
 bool load_weight_file(const char* path, std::map<std::string, HostTensor>& out, std::string& err) {
   FILE* f = fopen(path, "rb");
   if (!f) { err = std::string("cannot open weights file: ") + path; return false; }
+  struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+  if (fseek(f, 0, SEEK_END) != 0) { err = "cannot seek in weights file"; return false; }
+  const long file_size = ftell(f);
+  rewind(f);
   char magic[8];
   uint32_t count = 0;
-  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "UAHNWTS1", 8) != 0 || fread(&count, 4, 1, f) != 1) {
-    fclose(f); err = "bad weights file header"; return false;
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "UAHNWTS1", 8) != 0 || fread(&count, 4, 1, f) != 1 || count > 4096) {
+    err = "bad weights file header"; return false;
   }
   for (uint32_t i = 0; i < count; ++i) {
     uint32_t nl = 0, nd = 0;
-    if (fread(&nl, 4, 1, f) != 1 || nl > 256) { fclose(f); err = "bad tensor name"; return false; }
+    if (fread(&nl, 4, 1, f) != 1 || nl == 0 || nl > 256) { err = "bad tensor name"; return false; }
     std::string name(nl, '\0');
-    if (fread(&name[0], 1, nl, f) != nl || fread(&nd, 4, 1, f) != 1 || nd > 4) { fclose(f); err = "bad tensor header"; return false; }
+    if (fread(&name[0], 1, nl, f) != nl || fread(&nd, 4, 1, f) != 1 || nd > 4) { err = "bad tensor header"; return false; }
     HostTensor t;
     t.dims.resize(nd);
+    size_t numel = 1;
     for (uint32_t d = 0; d < nd; ++d) {
       uint32_t v;
-      if (fread(&v, 4, 1, f) != 1) { fclose(f); err = "bad dims"; return false; }
+      if (fread(&v, 4, 1, f) != 1 || v == 0 || v > (1u << 20)) { err = "bad dims of tensor " + name; return false; }
       t.dims[d] = (int)v;
+      numel *= v;
+      if (numel > (size_t(1) << 28)) { err = "tensor " + name + " is implausibly large"; return false; }
     }
-    t.data.resize(t.numel());
-    if (fread(t.data.data(), 4, t.data.size(), f) != t.data.size()) { fclose(f); err = "truncated tensor " + name; return false; }
+    const long pos = ftell(f);
+    if (pos < 0 || file_size < pos || (size_t)(file_size - pos) < numel * 4) { err = "truncated tensor " + name; return false; }
+    t.data.resize(numel);
+    if (fread(t.data.data(), 4, numel, f) != numel) { err = "truncated tensor " + name; return false; }
     out[name] = std::move(t);
   }
-  fclose(f);
   return true;
 }
 
@@ -114,6 +125,7 @@ struct uahn_handle {
   bool bf16 = false;
   size_t es = 4;
   int cap = 0;
+  int num_sms = 0;          // of cfg.device
   uint64_t launches = 0;
   std::vector<void*> allocs;
   Block blocks[5];
@@ -162,6 +174,8 @@ struct uahn_handle {
   uint8_t *s_prev[2] = {nullptr, nullptr}, *s_curr[2] = {nullptr, nullptr}, *s_frames[2] = {nullptr, nullptr};
   float *s_prior[2] = {nullptr, nullptr}, *s_mean[2] = {nullptr, nullptr}, *s_cov[2] = {nullptr, nullptr};
   uint64_t submit_count = 0;
+  bool pipeline_ready = false;
+  uint64_t auto_pair = 0;   // MC-dropout pair index of calls made with rng == NULL: fresh masks on every forward
   // per-category device timing (uahn_profile_*)
   struct ProfSpan { cudaEvent_t a, b; int cat; uint64_t launches; };
   bool prof_on = false;
@@ -414,8 +428,7 @@ int run_block(uahn_handle* h, Block& B, int n, const uint8_t* prev, const uint8_
   const size_t nl = B.layers.size();
   if (B.fused.enabled) {
     if constexpr (sizeof(T) == 2) {
-      static int num_sms = 0;
-      if (!num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+      const int num_sms = h->num_sms;
       h->prof_begin(0);
       LAUNCH(launch_warp_concat_pool<T>(prev, curr, Hcur, B.x, B.pool, n, st));
       h->prof_end();
@@ -540,7 +553,7 @@ extern "C" {
 
 int uahn_create(const uahn_config* cfg, uahn_handle** out) {
   if (!cfg || !out || !cfg->weights_path) { g_create_error = "null config / weights_path"; return UAHN_ERR_INVALID; }
-  if (cfg->variant < 0 || cfg->variant > 3 || cfg->precision < 0 || cfg->precision > 1 || cfg->max_batch < 1) {
+  if (cfg->variant < UAHN_VARIANT_AUTO || cfg->variant > 3 || cfg->precision < 0 || cfg->precision > 1 || cfg->max_batch < 1) {
     g_create_error = "invalid variant / precision / max_batch";
     return UAHN_ERR_INVALID;
   }
@@ -567,6 +580,7 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
   }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, cfg->device);
+  h->num_sms = prop.multiProcessorCount;
   if (prop.major != 10) {
     h->fail(UAHN_ERR_UNSUPPORTED, "device sm_%d%d: kernels are built for sm_100a only", prop.major, prop.minor);
     return bail(UAHN_ERR_UNSUPPORTED);
@@ -586,12 +600,31 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
   }
   std::map<std::string, HostTensor> w;
   std::string err;
-  if (!load_weight_file(cfg->weights_path, w, err)) {
+  bool loaded = false;
+  try {
+    loaded = load_weight_file(cfg->weights_path, w, err);
+  } catch (const std::exception& ex) {
+    err = std::string("weights file: ") + ex.what();
+  }
+  if (!loaded) {
     h->fail(UAHN_ERR_WEIGHTS, "%s", err.c_str());
     return bail(UAHN_ERR_WEIGHTS);
   }
+  // UAHN_VARIANT_AUTO: the exporter recorded which traced graph the file came from (weights.export_torchscript)
+  if (h->cfg.variant == UAHN_VARIANT_AUTO) {
+    auto it = w.find("__meta__.variant");
+    if (it == w.end() || it->second.data.size() != 1 || it->second.data[0] < 0 || it->second.data[0] > 3) {
+      h->fail(UAHN_ERR_WEIGHTS, "UAHN_VARIANT_AUTO: the weights file carries no variant record");
+      return bail(UAHN_ERR_WEIGHTS);
+    }
+    h->cfg.variant = (int)it->second.data[0];
+  }
+  if (h->cfg.show_error == UAHN_SHOW_ERROR_AUTO) {
+    auto it = w.find("__meta__.show_error");
+    h->cfg.show_error = (it != w.end() && it->second.data.size() == 1 && it->second.data[0] != 0.f) ? 1 : 0;
+  }
   int rc = UAHN_OK;
-  const int v = cfg->variant;
+  const int v = h->cfg.variant;
   if (v == UAHN_VARIANT_FULL && (rc = build_block(h, w, 1, B1, 3, 8))) return bail(rc);
   if ((v == UAHN_VARIANT_FULL || v == UAHN_VARIANT_PRIOR3) && (rc = build_block(h, w, 2, B2, 4, 4))) return bail(rc);
   if (v != UAHN_VARIANT_PRIOR1 && (rc = build_block(h, w, 3, B3, 6, 2))) return bail(rc);
@@ -619,7 +652,7 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
   if ((rc = dev_alloc(h, &h->d_prior, cap * 8))) return bail(rc);
   if ((rc = dev_alloc(h, &h->d_mean, cap * 8))) return bail(rc);
   if ((rc = dev_alloc(h, &h->d_cov, cap * 64))) return bail(rc);
-  if (cfg->show_error && (rc = dev_alloc(h, &h->d_err, cap * IMG_PIXELS))) return bail(rc);
+  if (h->cfg.show_error && (rc = dev_alloc(h, &h->d_err, cap * IMG_PIXELS))) return bail(rc);
   if ((rc = dev_alloc(h, &h->d_ring, (size_t)2 * IMG_PIXELS))) return bail(rc);
   if ((rc = dev_alloc(h, &h->d_rng, 2))) return bail(rc);
   h->use_graph = getenv("UAHN_NO_GRAPH") == nullptr;
@@ -671,6 +704,7 @@ int uahn_infer_batch_device(uahn_handle* h, int n, const uint8_t* prev, const ui
                             const uahn_rng* rng, float* mean, float* cov, float* err) {
   if (!h) return UAHN_ERR_INVALID;
   if (!prev || !curr || !mean || !cov) return h->fail(UAHN_ERR_INVALID, "null buffer");
+  if (err && !h->cfg.show_error) return h->fail(UAHN_ERR_INVALID, "err requested but handle created with show_error=0");
   CK(cudaSetDevice(h->cfg.device));
   return forward_any(h, n, prev, curr, prior, rng, rng ? rng->keep_masks : nullptr, mean, cov, err);
 }
@@ -708,20 +742,22 @@ int uahn_infer_batch(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* 
 namespace {
 // copy stream, events and the second staging set of the pipelined entry points
 int ensure_pipeline(uahn_handle* h) {
-  if (h->copy_stream) return UAHN_OK;
-  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  if (h->pipeline_ready) return UAHN_OK;
+  // a failure part-way leaves pipeline_ready false: the next submission retries only what is still missing
+  if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
-    CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    if (!h->ev_in[i]) CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+    if (!h->ev_done[i]) CK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
   }
   h->s_prev[0] = h->d_prev; h->s_curr[0] = h->d_curr; h->s_prior[0] = h->d_prior;
   h->s_mean[0] = h->d_mean; h->s_cov[0] = h->d_cov;
   int rc;
-  if ((rc = dev_alloc(h, &h->s_prev[1], (size_t)h->cap * IMG_PIXELS))) return rc;
-  if ((rc = dev_alloc(h, &h->s_curr[1], (size_t)h->cap * IMG_PIXELS))) return rc;
-  if ((rc = dev_alloc(h, &h->s_prior[1], (size_t)h->cap * 8))) return rc;
-  if ((rc = dev_alloc(h, &h->s_mean[1], (size_t)h->cap * 8))) return rc;
-  if ((rc = dev_alloc(h, &h->s_cov[1], (size_t)h->cap * 64))) return rc;
+  if (!h->s_prev[1] && (rc = dev_alloc(h, &h->s_prev[1], (size_t)h->cap * IMG_PIXELS))) return rc;
+  if (!h->s_curr[1] && (rc = dev_alloc(h, &h->s_curr[1], (size_t)h->cap * IMG_PIXELS))) return rc;
+  if (!h->s_prior[1] && (rc = dev_alloc(h, &h->s_prior[1], (size_t)h->cap * 8))) return rc;
+  if (!h->s_mean[1] && (rc = dev_alloc(h, &h->s_mean[1], (size_t)h->cap * 8))) return rc;
+  if (!h->s_cov[1] && (rc = dev_alloc(h, &h->s_cov[1], (size_t)h->cap * 64))) return rc;
+  h->pipeline_ready = true;
   return UAHN_OK;
 }
 
@@ -815,8 +851,10 @@ int uahn_infer(uahn_handle* h, const double* prior_px, const uahn_rng* rng, doub
     if (!prior_px) return h->fail(UAHN_ERR_INVALID, "this variant needs a prior");
     for (int i = 0; i < 8; ++i) h->h_prior[i] = (float)prior_px[i];        // HomographyNet.cpp:160-165 (.toType(kFloat))
   }
+  // rng == NULL: like the reference, which draws fresh masks on every forward (model_to_trace.py:266-273), every call
+  // gets its own Philox pair index from a per-handle counter
   h->h_rng[0] = rng ? rng->seed : 0;
-  h->h_rng[1] = rng ? rng->first_pair_index : 0;
+  h->h_rng[1] = rng ? rng->first_pair_index : h->auto_pair++;
   const uint8_t* dm = nullptr;
   if (rng && rng->keep_masks) {
     if (!h->d_masks) {
@@ -1000,21 +1038,43 @@ int uahn_stage_warp(uahn_handle* h, int n, const uint8_t* img, const float* Hm, 
   if (n <= 0 || n > h->cap) return h->fail(UAHN_ERR_INVALID, "n outside [1, max_batch]");
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = h->stream;
-  float* d_out = nullptr;
-  int16_t *d_ix = nullptr, *d_iy = nullptr;
-  CK(cudaMalloc(&d_out, (size_t)n * IMG_PIXELS * 4));
-  CK(cudaMalloc(&d_ix, (size_t)n * IMG_PIXELS * 2));
-  CK(cudaMalloc(&d_iy, (size_t)n * IMG_PIXELS * 2));
+  struct Scratch {   // freed on every exit path
+    float* out = nullptr; int16_t *ix = nullptr, *iy = nullptr;
+    ~Scratch() { cudaFree(out); cudaFree(ix); cudaFree(iy); }
+  } d;
+  CK(cudaMalloc(&d.out, (size_t)n * IMG_PIXELS * 4));
+  CK(cudaMalloc(&d.ix, (size_t)n * IMG_PIXELS * 2));
+  CK(cudaMalloc(&d.iy, (size_t)n * IMG_PIXELS * 2));
   CK(cudaMemcpyAsync(h->d_curr, img, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->Hb[0], Hm, (size_t)n * 36, cudaMemcpyHostToDevice, st));
-  LAUNCH(launch_warp_plain(h->d_curr, h->d_curr, h->Hb[0], d_out, nullptr, d_ix, d_iy, 0, n, st));
-  CK(cudaMemcpyAsync(out, d_out, (size_t)n * IMG_PIXELS * 4, cudaMemcpyDeviceToHost, st));
-  if (ix_nw) CK(cudaMemcpyAsync(ix_nw, d_ix, (size_t)n * IMG_PIXELS * 2, cudaMemcpyDeviceToHost, st));
-  if (iy_nw) CK(cudaMemcpyAsync(iy_nw, d_iy, (size_t)n * IMG_PIXELS * 2, cudaMemcpyDeviceToHost, st));
+  LAUNCH(launch_warp_plain(h->d_curr, h->d_curr, h->Hb[0], d.out, nullptr, d.ix, d.iy, 0, n, st));
+  CK(cudaMemcpyAsync(out, d.out, (size_t)n * IMG_PIXELS * 4, cudaMemcpyDeviceToHost, st));
+  if (ix_nw) CK(cudaMemcpyAsync(ix_nw, d.ix, (size_t)n * IMG_PIXELS * 2, cudaMemcpyDeviceToHost, st));
+  if (iy_nw) CK(cudaMemcpyAsync(iy_nw, d.iy, (size_t)n * IMG_PIXELS * 2, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  cudaFree(d_out); cudaFree(d_ix); cudaFree(d_iy);
   return UAHN_OK;
 }
+
+// model_to_trace.py:18-38 + :311-317 alone: var, pts_w n x 8, Hp n x 9 (HOST) -> flow n x 8, cov n x 64
+int uahn_stage_transfer(uahn_handle* h, int n, const float* var, const float* Hp, const float* pts_w, float* flow,
+                        float* cov) {
+  if (!h || !var || !Hp || !pts_w || !flow || !cov) return UAHN_ERR_INVALID;
+  if (n <= 0 || n > h->cap) return h->fail(UAHN_ERR_INVALID, "n outside [1, max_batch]");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  // scratch: var -> dblk[1], pts_w -> dblk[2], Hp -> Hb[0]; results in the regular output staging
+  CK(cudaMemcpyAsync(h->dblk[1], var, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->dblk[2], pts_w, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->Hb[0], Hp, (size_t)n * 36, cudaMemcpyHostToDevice, st));
+  LAUNCH(launch_transfer(n, h->dblk[1], h->Hb[0], h->dblk[2], h->d_mean, h->d_cov, st));
+  CK(cudaMemcpyAsync(flow, h->d_mean, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(cov, h->d_cov, (size_t)n * 256, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return UAHN_OK;
+}
+
+int uahn_variant(const uahn_handle* h) { return h ? h->cfg.variant : UAHN_ERR_INVALID; }
+int uahn_show_error(const uahn_handle* h) { return h ? h->cfg.show_error : UAHN_ERR_INVALID; }
 
 int uahn_stage_conv(uahn_handle* h, const char* layer, int n, const float* in_nchw) {
   if (!h || !layer || !in_nchw) return UAHN_ERR_INVALID;

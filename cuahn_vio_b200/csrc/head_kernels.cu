@@ -339,6 +339,49 @@ __global__ void __launch_bounds__(256) mc_maskbits_kernel(uint8_t* __restrict__ 
   }
 }
 
+// transfer_mean_var_single for corner i (model_to_trace.py:18-38) + output packing (:311-317): projects the block-4 point
+// (u, v) through the part-1 homography Hp, writes flow[2i..2i+1] = p/s - corner and rows 2i, 2i+1 of the block-diagonal
+// 8x8 covariance, Cov_i = ((Hp/s) diag(vu, vv, 0) (Hp/s)^T)[0:2, 0:2], in the reference's fp32 operation order.
+__device__ __forceinline__ void transfer_point(int i, const float* Hp, float u, float v, float vu, float vv, float* mean8,
+                                               float* cov64) {
+  float p[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    p[r] = __fmaf_rn(Hp[r * 3 + 2], 1.f, __fmaf_rn(Hp[r * 3 + 1], v, __fmul_rn(Hp[r * 3], u)));
+  const float sc = p[2];
+  float x0, y0;
+  corner(i, x0, y0);
+  mean8[2 * i] = __fsub_rn(__fdiv_rn(p[0], sc), x0);          // model_to_trace.py:311
+  mean8[2 * i + 1] = __fsub_rn(__fdiv_rn(p[1], sc), y0);
+  float Hs[9];
+#pragma unroll
+  for (int r = 0; r < 9; ++r) Hs[r] = __fdiv_rn(Hp[r], sc);   // model_to_trace.py:30
+  float c2[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const float t0 = __fmul_rn(Hs[a * 3], vu), t1 = __fmul_rn(Hs[a * 3 + 1], vv);
+      c2[a][b] = __fmaf_rn(t1, Hs[b * 3 + 1], __fmul_rn(t0, Hs[b * 3]));   // third term is exactly 0
+    }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) cov64[(2 * i + a) * 8 + b] = (b >> 1) == i ? c2[a][b & 1] : 0.f;
+}
+
+// stage entry point (parity tests): the covariance transfer alone, one thread per (pair, corner)
+__global__ void transfer_kernel(int n, const float* __restrict__ var, const float* __restrict__ Hp, const float* __restrict__ pts_w,
+                                float* __restrict__ mean, float* __restrict__ cov) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, pair = t >> 2, i = t & 3;
+  if (pair >= n) return;
+  float H[9];
+#pragma unroll
+  for (int r = 0; r < 9; ++r) H[r] = Hp[pair * 9 + r];
+  transfer_point(i, H, pts_w[pair * 8 + 2 * i], pts_w[pair * 8 + 2 * i + 1], var[pair * 8 + 2 * i], var[pair * 8 + 2 * i + 1],
+                 mean + pair * 8, cov + (size_t)pair * 64);
+}
+
 struct HeadOut {
   float* mean;     // [n][8]
   float* cov;      // [n][64]
@@ -445,36 +488,8 @@ __global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid
       ptsw[2 * i] = __fadd_rn(x, mu_s[2 * i]);          // model_to_trace.py:281
       ptsw[2 * i + 1] = __fadd_rn(y, mu_s[2 * i + 1]);
     }
-    if (lane < 4) {                                     // transfer_mean_var_single, one point per lane
-      const int i = lane;
-      const float u = ptsw[2 * i], v = ptsw[2 * i + 1];
-      float p[3];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-        p[r] = __fmaf_rn(Hp[r * 3 + 2], 1.f, __fmaf_rn(Hp[r * 3 + 1], v, __fmul_rn(Hp[r * 3], u)));
-      const float sc = p[2];
-      float x0, y0;
-      corner(i, x0, y0);
-      o.mean[pair * 8 + 2 * i] = __fsub_rn(__fdiv_rn(p[0], sc), x0);          // model_to_trace.py:311
-      o.mean[pair * 8 + 2 * i + 1] = __fsub_rn(__fdiv_rn(p[1], sc), y0);
-      float Hs[9];
-#pragma unroll
-      for (int r = 0; r < 9; ++r) Hs[r] = __fdiv_rn(Hp[r], sc);               // model_to_trace.py:30
-      const float vu = var_s[2 * i], vv = var_s[2 * i + 1];
-      float c2[2][2];
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const float t0 = __fmul_rn(Hs[a * 3], vu), t1 = __fmul_rn(Hs[a * 3 + 1], vv);
-          c2[a][b] = __fmaf_rn(t1, Hs[b * 3 + 1], __fmul_rn(t0, Hs[b * 3]));   // third term is exactly 0
-        }
-      float* cv = o.cov + (size_t)pair * 64;
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) cv[(2 * i + a) * 8 + b] = (b >> 1) == i ? c2[a][b & 1] : 0.f;
-    }
+    if (lane < 4) transfer_point(lane, Hp, ptsw[2 * lane], ptsw[2 * lane + 1], var_s[2 * lane], var_s[2 * lane + 1],
+                                 o.mean + pair * 8, o.cov + (size_t)pair * 64);
     if (o.Htot) {                                       // model_to_trace.py:321-323
       double h4[9];
       dlt_warp(ptsw, h4);
@@ -491,6 +506,12 @@ __global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid
 }
 
 }  // namespace
+
+cudaError_t launch_transfer(int n, const float* var, const float* Hp, const float* pts_w, float* mean, float* cov,
+                            cudaStream_t st) {
+  transfer_kernel<<<(4 * n + 127) / 128, 128, 0, st>>>(n, var, Hp, pts_w, mean, cov);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_dlt(int n, const float* off, const float* Hprev, float* Hout, cudaStream_t st) {
   const int threads = 128, pairs_per_block = threads / 32;

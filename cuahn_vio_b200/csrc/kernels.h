@@ -21,6 +21,9 @@ cudaError_t launch_conv_f32(const float* in, const float* wk, const float* bias,
                             cudaStream_t st);
 
 // head_kernels.cu
+// transfer_mean_var_single + packing for n pairs: var, pts_w [n][8], Hp [n][9] -> flow [n][8], cov [n][64]
+cudaError_t launch_transfer(int n, const float* var, const float* Hp, const float* pts_w, float* mean, float* cov,
+                            cudaStream_t st);
 cudaError_t launch_dlt(int n, const float* off, const float* Hprev, float* Hout, cudaStream_t st);
 template <typename T>
 cudaError_t launch_fc8_dlt(int n, const T* feat, const float* W8, const float* b8, const float* Hprev, float* Hout,

@@ -36,7 +36,8 @@ namespace pytorch {
 class HomographyNet {
  public:
   HomographyNet(std::string& network_model_path, std::string& network_model_iterative_path, bool use_prior,
-                int num_of_iteration, bool show_imgs, int precision = UAHN_PRECISION_BF16, int device = 0) {
+                int num_of_iteration, bool show_imgs, int precision = UAHN_PRECISION_BF16, int device = 0,
+                int iterative_variant = UAHN_VARIANT_AUTO) {
     use_prior_4pt_offset = use_prior;
     cv_imshow = show_imgs;
     std::cout << "CUDA (sm_100a) UAHN engine: running on GPU " << device << "." << std::endl;
@@ -46,7 +47,13 @@ class HomographyNet {
     if (num_of_iteration > 1) {                                                           // HomographyNet.cpp:20-24
       iteration = true;
       const bool it_err = network_model_iterative_path.find("_showError") != std::string::npos;
-      iter_ = create(network_model_iterative_path, UAHN_VARIANT_PRIOR2, it_err, precision, device);
+      // The reference's second slot runs whatever graph the file holds (HomographyNet.cpp:104-124; blocks_to_run in
+      // {1, 2, 3}, model_to_trace.py:72,131-132).  UAHN_VARIANT_AUTO takes the variant the exporter recorded in the flat
+      // file (weights.export_torchscript); files without a record (exported from a bare checkpoint) fall back to the
+      // 2-block schedule.
+      iter_ = create(network_model_iterative_path, iterative_variant, it_err, precision, device, /*quiet=*/iterative_variant == UAHN_VARIANT_AUTO);
+      if (!iter_ && iterative_variant == UAHN_VARIANT_AUTO)
+        iter_ = create(network_model_iterative_path, UAHN_VARIANT_PRIOR2, it_err, precision, device);
       std::cout << "IEKF! Load the Network for Iteration!" << std::endl;
     }
     // warm-up forward on constant images 0.2 / 0.5 and an all-ones prior (HomographyNet.cpp:29-63)
@@ -113,7 +120,7 @@ class HomographyNet {
     }
     uahn_handle* h = (num_of_inference == 0 || !iter_) ? main_ : iter_;
     if (!h) { std::cerr << "error loading the model !!!\n"; return; }
-    uahn_rng rng{seed_, inference_counting, nullptr};
+    uahn_rng rng{seed_, rng_calls_++, nullptr};   // every forward draws fresh masks (model_to_trace.py:266-273)
     const bool want_err = cv_imshow && show_phtometric_error && (num_of_inference != 0 || !iteration);
     const auto t0 = std::chrono::steady_clock::now();
     double mean[8], cov[64];
@@ -139,7 +146,8 @@ class HomographyNet {
   void set_seed(uint64_t s) { seed_ = s; }
 
  private:
-  static uahn_handle* create(const std::string& path, int variant, bool show_err, int precision, int device) {
+  static uahn_handle* create(const std::string& path, int variant, bool show_err, int precision, int device,
+                             bool quiet = false) {
     std::cout << "Loading the Network Model (UAHN flat weights) ..." << std::endl;
     uahn_config cfg{};
     cfg.weights_path = path.c_str();
@@ -150,7 +158,7 @@ class HomographyNet {
     cfg.max_batch = 1;
     uahn_handle* h = nullptr;
     if (uahn_create(&cfg, &h) != UAHN_OK) {   // print-and-continue like HomographyNet.cpp:87-93
-      std::cerr << "error loading the model !!! " << uahn_last_error(nullptr) << "\n";
+      if (!quiet) std::cerr << "error loading the model !!! " << uahn_last_error(nullptr) << "\n";
       return nullptr;
     }
     std::cerr << path << std::endl;
@@ -160,6 +168,7 @@ class HomographyNet {
   uahn_handle* main_ = nullptr;
   uahn_handle* iter_ = nullptr;
   uint64_t inference_counting = 0;
+  uint64_t rng_calls_ = 0;
   uint64_t seed_ = 0;
   int warmup_images_ = 0;
   bool cv_imshow = false, use_prior_4pt_offset = false, show_phtometric_error = false, iteration = false;

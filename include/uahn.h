@@ -49,6 +49,8 @@ enum {
 
 /* Which traced graph of trace_model.py:36-46 the handle reproduces. */
 enum {
+  UAHN_VARIANT_AUTO = -1,   /* whatever graph the weights file was exported from (weights.export_torchscript records
+                               it): the reference's iterative slot runs "whatever the file holds", HomographyNet.cpp:104-124 */
   UAHN_VARIANT_FULL = 0,    /* traced_full_model: blocks 1+2+3+4, no prior            */
   UAHN_VARIANT_PRIOR3 = 1,  /* traced_model_3_blocks_using_prior: prior + blocks 2,3,4 */
   UAHN_VARIANT_PRIOR2 = 2,  /* blocks_to_run = 2 (model_to_trace.py:72): prior + blocks 3,4 */
@@ -59,6 +61,8 @@ enum {
   UAHN_PRECISION_FP32 = 0,  /* validation mode: true fp32 FFMA convolutions           */
   UAHN_PRECISION_BF16 = 1   /* tcgen05 bf16 implicit-GEMM convolutions, fp32 accumulate */
 };
+
+#define UAHN_SHOW_ERROR_AUTO (-1) /* uahn_config.show_error: take the `_showError` flag recorded in the weights file */
 
 typedef struct uahn_handle uahn_handle;
 
@@ -76,7 +80,11 @@ typedef struct uahn_config {
  * keep_masks == NULL: masks are drawn in-kernel from Philox4x32-7 keyed by (seed, first_pair_index + i).
  * keep_masks != NULL: explicit replay; HOST (or device, for the *_device call) bytes, 1 = kept, 0 = dropped,
  *   laid out [pair][head(0=mean,1=uncertainty)][sample 0..15][5120 inputs, then 256 hidden], the 5120 axis
- *   in the reference's NCHW flatten order c*20 + h*5 + w.  Kept values are scaled by 1/0.95. */
+ *   in the reference's NCHW flatten order c*20 + h*5 + w.  Kept values are scaled by 1/0.95.
+ * A NULL uahn_rng* means seed 0; uahn_infer then numbers its calls itself (a per-handle counter is the pair index), so
+ * consecutive frames and IEKF iterations draw different masks, as the reference's forward does.  The batch entry
+ * points use pair index first_pair_index + i; passing the same (seed, first_pair_index) twice REPLAYS the same masks —
+ * advance first_pair_index by n per call for fresh ones. */
 typedef struct uahn_rng {
   uint64_t seed;
   uint64_t first_pair_index;
@@ -127,6 +135,8 @@ UAHN_API void* uahn_stream(uahn_handle* h);
 UAHN_API uint64_t uahn_launch_count(const uahn_handle* h);
 UAHN_API double uahn_latest_inference_time(const uahn_handle* h); /* HomographyNet::get_latest_inference_time */
 UAHN_API int uahn_image_count(const uahn_handle* h);               /* HomographyNet::img_counter */
+UAHN_API int uahn_variant(const uahn_handle* h);    /* the resolved UAHN_VARIANT_* (after UAHN_VARIANT_AUTO) */
+UAHN_API int uahn_show_error(const uahn_handle* h); /* the resolved show_error flag */
 
 /* Per-stage device timing (bench.py's roofline): when enabled, every forward brackets each kernel group with
  * CUDA events on the handle's stream.  Categories: 0 = warp/concat/pool + error map (HBM-bound),
@@ -145,6 +155,10 @@ UAHN_API int uahn_stage_dlt(uahn_handle* h, int n, const float* offsets, float* 
 /* warp.py:60-79: img n x 224 x 320 u8, H n x 9 -> out n x 224 x 320 float; optional NW tap indices. */
 UAHN_API int uahn_stage_warp(uahn_handle* h, int n, const uint8_t* img, const float* H, float* out, int16_t* ix_nw,
                     int16_t* iy_nw);
+/* model_to_trace.py:18-38 (transfer_mean_var_single) + the output packing of :311-317: var n x 8 (sigma^2 per corner
+ * coordinate), Hp n x 9 (part-1 homography), pts_w n x 8 (corners + mu) -> flow n x 8, cov n x 64. */
+UAHN_API int uahn_stage_transfer(uahn_handle* h, int n, const float* var, const float* Hp, const float* pts_w, float* flow,
+                        float* cov);
 /* One Conv2d+LeakyReLU layer of the handle's precision path: `layer` e.g. "block_3_1"; in: n x Cin x Hin x Win
  * float (NCHW); the result is read back with uahn_debug_read("act:<layer>") as n x Cout x Ho x Wo. */
 UAHN_API int uahn_stage_conv(uahn_handle* h, const char* layer, int n, const float* in_nchw);

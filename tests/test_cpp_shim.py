@@ -46,3 +46,14 @@ def test_shim_matches_c_abi(tmp_path):
     for r, m, c in ((res[1], m1, c1), (res[2], m2, c2)):
         assert np.allclose(np.array(r[4:12], float), m[0], atol=1e-6)
         assert np.allclose(np.array(r[12:20], float), np.diag(c[0]), rtol=1e-6)
+
+
+def test_reference_signature_flavour_type_checks():
+    """`-DUAHN_WITH_EIGEN_OPENCV` (cv::Mat / Eigen::Matrix signatures of HomographyNet.h:26-32) against VioManager's call
+    pattern, with the minimal stub headers under tests/cpp/stubs: the container has neither Eigen nor OpenCV, so this
+    is a syntax + type check (`-fsyntax-only`), not a link."""
+    cmd = ["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-Werror", "-DUAHN_WITH_EIGEN_OPENCV",
+           "-I", os.path.join(ROOT, "tests", "cpp", "stubs"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "shim_reference_signatures.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
