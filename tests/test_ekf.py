@@ -124,7 +124,7 @@ def test_iekf_frame_loop():
         net.iekf_frame(st, max_iter=2, min_images=0, seed=3, pair_index=0)
         imu2, off2, P2 = st.arrays()
         i_r, o_r, P_r = E.update(imu, off, P, m_ref, c_ref, off[:, :2].reshape(8), True, 10.0)
-        m2, c2, _ = net.infer(o_r[:, :2].reshape(8) * 159.5, seed=3, pair_index=0)
+        m2, c2, _ = net.infer(o_r[:, :2].reshape(8) * 159.5, seed=3, pair_index=1)   # iteration `it` draws pair index first_pair_index + it
         i_r, o_r, P_r = E.update(i_r, o_r, P_r, m2, c2, o_r[:, :2].reshape(8), False, 10.0)
         o_r, P_r = E.reset_4pt_offset(o_r, P_r)
         assert np.abs(imu2 - i_r).max() < 1e-10 and np.array_equal(off2, o_r)
