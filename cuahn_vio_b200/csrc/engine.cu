@@ -531,7 +531,7 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
   h->prof_end();
   if (want_err) {
     h->prof_begin(0);
-    LAUNCH(launch_warp_plain(prev, curr, h->Htot, err_u8 ? nullptr : err, err_u8, nullptr, nullptr, 1, n, st));
+    LAUNCH(launch_warp_plain(prev, curr, h->Htot, err_u8 ? nullptr : err, err_u8, nullptr, nullptr, 1, n, st, sizeof(T) == 2));
     h->prof_end();
   }
   h->last_n = n;
@@ -1047,7 +1047,7 @@ int uahn_stage_warp(uahn_handle* h, int n, const uint8_t* img, const float* Hm, 
   CK(cudaMalloc(&d.iy, (size_t)n * IMG_PIXELS * 2));
   CK(cudaMemcpyAsync(h->d_curr, img, (size_t)n * IMG_PIXELS, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->Hb[0], Hm, (size_t)n * 36, cudaMemcpyHostToDevice, st));
-  LAUNCH(launch_warp_plain(h->d_curr, h->d_curr, h->Hb[0], d.out, nullptr, d.ix, d.iy, 0, n, st));
+  LAUNCH(launch_warp_plain(h->d_curr, h->d_curr, h->Hb[0], d.out, nullptr, d.ix, d.iy, 0, n, st, h->bf16));   // the handle's own coordinate mode
   CK(cudaMemcpyAsync(out, d.out, (size_t)n * IMG_PIXELS * 4, cudaMemcpyDeviceToHost, st));
   if (ix_nw) CK(cudaMemcpyAsync(ix_nw, d.ix, (size_t)n * IMG_PIXELS * 2, cudaMemcpyDeviceToHost, st));
   if (iy_nw) CK(cudaMemcpyAsync(iy_nw, d.iy, (size_t)n * IMG_PIXELS * 2, cudaMemcpyDeviceToHost, st));

@@ -9,8 +9,10 @@ template <typename T>
 cudaError_t launch_warp_concat_pool(const uint8_t* prev, const uint8_t* curr, const float* Hmat, const Tensor& out,
                                     int pool, int n, cudaStream_t st);
 // out (float) or out_u8 (error map clamped to [0,255] and truncated, HomographyNet.cpp:201) — exactly one is non-null
+// allow_fast: the bf16 product path's coordinate mode (image_kernels.cu CM_FAST: fast coordinates, exact fallback near
+// integer boundaries — indices stay bit-exact); 0 = the exact chain everywhere (fp32 validation mode)
 cudaError_t launch_warp_plain(const uint8_t* prev, const uint8_t* curr, const float* Hmat, float* out, uint8_t* out_u8,
-                              int16_t* ix, int16_t* iy, int error_map, int n, cudaStream_t st);
+                              int16_t* ix, int16_t* iy, int error_map, int n, cudaStream_t st, int allow_fast);
 
 // cv::remap(INTER_LINEAR, constant-0 border) of a raw u8 frame through float maps into a 224x320 u8 image
 cudaError_t launch_remap_u8(const uint8_t* raw, int rows, int cols, const float* map1, const float* map2, uint8_t* out,

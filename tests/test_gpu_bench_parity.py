@@ -253,3 +253,24 @@ def test_handles_on_two_devices_in_one_process(api, wfile):
                 outs.append((precision, net.infer_batch(prev, curr, prior, seed=1, want_error=True)))
     for (p0, a), (p1, b) in zip(outs[:2], outs[2:]):
         assert p0 == p1 and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_fast_coordinate_path_indices_bit_exact_over_18M_coordinates(api, wfile, golden_stages):
+    """The bf16 product path's warp (CM_FAST: 3 FMAs + MUFU.RCP coordinates, exact chain only near integer boundaries)
+    against the reference's index arithmetic over 256 random homographies in the benchmark's displacement range."""
+    g = golden_stages
+    rng = np.random.default_rng(2024)
+    n = 256
+    Hs = np.stack([S.dlt_numpy(S.ORIGIN_4PT.astype(np.float64), S.ORIGIN_4PT + (rng.random((4, 2)) * 2 - 1) * 20).astype(np.float32)
+                   for _ in range(n)])
+    img = np.repeat(g["warp_src_u8"][None], n, 0)
+    with api.Uahn(wfile, "prior1", precision="bf16", max_batch=n) as net:
+        _, ix, iy = net.stage_warp(img, Hs)
+    mism = checked = 0
+    for t in range(n):
+        rix, riy, _, _ = O.sample_indices(torch.from_numpy(Hs[t]))
+        rix, riy = rix.numpy(), riy.numpy()
+        inside = (rix >= -1) & (rix <= 320) & (riy >= -1) & (riy <= 224)
+        mism += int((ix[t][inside] != rix[inside]).sum() + (iy[t][inside] != riy[inside]).sum())
+        checked += 2 * int(inside.sum())
+    assert mism == 0 and checked > 30_000_000, (mism, checked)

@@ -63,13 +63,18 @@ def test_stage_dlt_matches_reference(api, wfile, golden_stages):
             assert np.abs((p[:2] / p[2]).T - (S.ORIGIN_4PT + off[i])).max() < 2e-3
 
 
-def test_stage_warp_indices_bit_exact(api, wfile, golden_stages):
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_stage_warp_indices_bit_exact(api, wfile, golden_stages, precision):
+    """fp32 handle: the exact coordinate chain.  bf16 handle: the product path's fast coordinates with the exact fallback
+    near integer boundaries (image_kernels.cu CM_FAST) — the indices must be just as bit-exact; its bilinear weights may
+    move by 3e-4 px, i.e. 3e-4 x the local grey-level step in value."""
     g = golden_stages
-    with api.Uahn(wfile, "prior1", max_batch=32) as net:
+    vtol = 2e-6 if precision == "fp32" else 4e-4
+    with api.Uahn(wfile, "prior1", precision=precision, max_batch=32) as net:
         img = np.repeat(g["warp_src_u8"][None], 4, 0)
         out, ix, iy = net.stage_warp(img, g["warp_H"])
         assert np.array_equal(ix, g["warp_ix"]) and np.array_equal(iy, g["warp_iy"])   # fixtures from the reference
-        assert np.abs(out - g["warp_out"]).max() < 2e-6
+        assert np.abs(out - g["warp_out"]).max() < vtol
         # random homographies incl. large ones that leave the image; oracle computed here
         rng = np.random.default_rng(11)
         Hs = []
@@ -87,8 +92,18 @@ def test_stage_warp_indices_bit_exact(api, wfile, golden_stages):
             rix, riy, _, _ = O.sample_indices(Ht)
             inside = (rix.numpy() >= -1) & (rix.numpy() <= 320) & (riy.numpy() >= -1) & (riy.numpy() <= 224)
             mism += int((ix[t][inside] != rix.numpy()[inside]).sum() + (iy[t][inside] != riy.numpy()[inside]).sum())
-            assert np.abs(out[t] - O.warp_image(src, Ht)[0, 0].numpy()).max() < 2e-6
+            assert np.abs(out[t] - O.warp_image(src, Ht)[0, 0].numpy()).max() < vtol
         assert mism == 0
+        # integer translations: every sample sits exactly on a pixel (the fast path's worst case: all fallbacks)
+        Ht = np.stack([np.eye(3, dtype=np.float32)] * 3)
+        Ht[1, 0, 2], Ht[1, 1, 2] = 5.0, -3.0
+        Ht[2, 0, 2], Ht[2, 1, 2] = -17.0, 40.0
+        out, ix, iy = net.stage_warp(img8[:3], Ht)
+        for t in range(3):
+            rix, riy, _, _ = O.sample_indices(torch.from_numpy(Ht[t]))
+            inside = (rix.numpy() >= -1) & (rix.numpy() <= 320) & (riy.numpy() >= -1) & (riy.numpy() <= 224)
+            assert np.array_equal(ix[t][inside], rix.numpy()[inside]) and np.array_equal(iy[t][inside], riy.numpy()[inside])
+            assert np.abs(out[t] - O.warp_image(src, torch.from_numpy(Ht[t]))[0, 0].numpy()).max() < vtol
 
 
 def test_warp_identity_and_outside(api, wfile):
