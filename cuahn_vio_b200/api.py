@@ -124,7 +124,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or _LIB_PATH
+    p = path or os.environ.get("UAHN_LIB_PATH") or _LIB_PATH     # UAHN_LIB_PATH: A/B runs against another build
     if not os.path.exists(p):
         raise UahnError(f"{p} not found: build it first (python cuahn_vio_b200/build.py); there is no CPU fallback")
     lib = C.CDLL(p)

@@ -14,7 +14,8 @@ ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--rounds", type=int, default=5)
 ap.add_argument("--tag", default="")
 a = ap.parse_args()
-build.build()
+if not os.environ.get("UAHN_LIB_PATH"):
+    build.build()
 dev = torch.device("cuda", 0)
 n = a.batch
 hp, hc, _, hpr = S.tiled_batch(n, unique=16)
