@@ -5,11 +5,11 @@
 //
 // Tile = 7 x 14 patch of conv-2 pixel groups (one group = 64/C2 output pixels = G1 = 64/C1 conv-1 pixels = one
 // 128-byte K row).  Per tile and CTA:
-//   1. TMA: one 4-D box {64 el, 8 groups, 38 rows} of the 2-channel block input (overlapping x windows, halo 5),
-//      double-buffered and fetched a tile ahead.
+//   1. TMA: one 4-D box {32 el, 8 groups, 38 rows} of the 2-channel block input (overlapping x windows, halo 5;
+//      64-byte rows, SWIZZLE_64B), double-buffered and fetched a tile ahead.
 //   2. conv 1 as ONE 128-row MMA tile with N = 128: GEMM row (t, g) = conv-1 row PAIR 2t, 2t+1 of group g — Toeplitz
 //      expansion in y as well as in x.  Window row j = 0..7 of the pair is the same input plane shifted by j rows with the
-//      8-row atoms of the A descriptor two input rows apart (SBO = 2048 B), so A still comes straight from the TMA box;
+//      8-row atoms of the A descriptor two input rows apart (SBO = 1024 B), so A still comes straight from the TMA box;
 //      B1[j] holds W1[ky = j - r] for output row r = 0, 1 in columns r*64 .. r*64+63.  16 MMAs of N = 128 replace the 28
 //      of N = 64 of the one-row formulation: at N = 64 the tensor core waits on its shared-memory operand fetch (4 KB of A
 //      per 32 cycles of math, ncu: l1tex__data_pipe_tc_wavefronts_mem_shared 89 %), at N = 128 the same A bytes feed 64
@@ -43,7 +43,10 @@ constexpr int FF_EPI1_WARPS = 8;                     // conv-1 epilogue: 2 per T
 constexpr int FF_EPI2_WARPS = 8;                     // conv-2 epilogue: 2 per quadrant, 32 columns each
 constexpr int FF_THREADS = 64 + 32 * (FF_EPI1_WARPS + FF_EPI2_WARPS);
 constexpr int IN_ROWS = 38;                          // 32 conv-1 rows + 6 (7x7 halo)
-constexpr int IN_BYTES = IN_ROWS * 8 * 128;          // 38 912
+// input plane: per (row, group) the first 32 elements of the group's x window (14 / 10 pixels x 2 channels are used):
+// 64-byte rows, SWIZZLE_64B — half the shared-memory writes and L2 reads of a 128-byte-row plane
+constexpr int IN_ROW_BYTES = 8 * 64;                 // one image row of the plane: 8 groups x 64 B = one 8-row swizzle atom
+constexpr int IN_BYTES = IN_ROWS * IN_ROW_BYTES;     // 19 456
 constexpr int B1_STAGES = 4, B2_STAGES = 10;         // 8 window rows packed in pairs; 5 taps x 2 chunks
 constexpr int B1_STAGE = 128 * 128, B2_STAGE = 64 * 128;   // full stages: N = 128 / 64 rows x 128 B
 constexpr int BST1 = B1_STAGE / 2, BST2 = B2_STAGE / 2;    // this CTA's half of the N rows
@@ -198,7 +201,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
     // K-major SW128 descriptors: LBO = 1 (unused), version 1, layout 2; SBO = bytes between 8-row atoms
     constexpr uint64_t DESC_BASE = (1ull << 16) | (1ull << 46) | (2ull << 61);
     constexpr uint64_t DESC_SBO1K = DESC_BASE | ((uint64_t)(1024 >> 4) << 32);
-    constexpr uint64_t DESC_SBO2K = DESC_BASE | ((uint64_t)(2048 >> 4) << 32);   // conv-1 A: GEMM row t -> input row 2t + j
+    // conv-1 A: K-major SWIZZLE_64B (layout 4), 8-row atoms (one image row of the plane, 512 B) two image rows apart:
+    // GEMM row (t, g) of window row j reads image row 2t + j
+    constexpr uint64_t DESC_A1 = (1ull << 16) | (1ull << 46) | (4ull << 61) | ((uint64_t)((2 * IN_ROW_BYTES) >> 4) << 32);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t in16 = (smem_u32(sIn) & 0x3FFFFu) >> 4, b1_16 = (smem_u32(sB1) & 0x3FFFFu) >> 4;
     const uint32_t b2_16 = (smem_u32(sB2) & 0x3FFFFu) >> 4, pl16 = (smem_u32(sPl) & 0x3FFFFu) >> 4;
@@ -213,9 +218,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv_fused_front_kernel(const _
         for (int j = 0; j < 8; ++j)                                   // window row j of the conv-1 row pair
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
-            const uint32_t alo = in16 + (uint32_t)(buf * (IN_BYTES / 16) + j * (8 * 128 / 16) + kk * 2);
+            const uint32_t alo = in16 + (uint32_t)(buf * (IN_BYTES / 16) + j * (IN_ROW_BYTES / 16) + kk * 2);
             const uint32_t blo = b1_16 + (uint32_t)((j >> 1) * (BST1 / 16) + (j & 1) * 4 + kk * 2);
-            tc_mma_bf16_pair(tmem_u + (uint32_t)(buf * 128), DESC_SBO2K | (uint64_t)alo, DESC_SBO1K | (uint64_t)blo, idesc1, 1u);
+            tc_mma_bf16_pair(tmem_u + (uint32_t)(buf * 128), DESC_A1 | (uint64_t)alo, DESC_SBO1K | (uint64_t)blo, idesc1, 1u);
           }
         tc_commit_pair(BAR(B_D1_FULL + buf));
         tc_commit_pair(BAR(B_IN_EMPTY + buf));                        // this input buffer may be refilled
@@ -388,14 +393,14 @@ int conv_fused_prepare(FusedPlan& plan, const std::vector<float>& wk0, const std
   plan.TY = g1.Ho / 14;
   plan.Wox2 = g1.Wo / xb2;
   plan.H1 = g0.Ho; plan.W1 = g0.Wo;
-  // ---- tensor map over the block input: {64 el window, conv-1 group, padded row, image} ----
+  // ---- tensor map over the block input: {32 el window, conv-1 group, padded row, image} ----
   PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode_ff();
   if (!encode) { err = "cuTensorMapEncodeTiled entry point not found"; return -2; }
-  const cuuint64_t gdim[4] = {64, 48, (cuuint64_t)x.Hp, (cuuint64_t)x.N};
+  const cuuint64_t gdim[4] = {32, 48, (cuuint64_t)x.Hp, (cuuint64_t)x.N};
   const cuuint64_t gstr[3] = {(cuuint64_t)G1 * 2 * 2, (cuuint64_t)x.pitch_y() * 2, (cuuint64_t)x.pitch_n * 2};
-  const cuuint32_t box[4] = {64, 8, IN_ROWS, 1}, estr[4] = {1, 1, 1, 1};
+  const cuuint32_t box[4] = {32, 8, IN_ROWS, 1}, estr[4] = {1, 1, 1, 1};
   if (encode(reinterpret_cast<CUtensorMap*>(plan.tmap), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x.p, gdim, gstr, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return 0;
   // ---- B1: window rows j = 0..7 of a conv-1 row PAIR, two per 64-element stage; N = 128:
