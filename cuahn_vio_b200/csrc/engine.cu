@@ -494,7 +494,12 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
   // or two M tiles the fused producer is a serial latency chain (80 K-stages per tile) and the plain GEMM, split over N
   // tiles, finishes sooner.
   const bool fused_mc = sizeof(T) == 2 && n >= MC_FUSED_MIN_PAIRS;
-  if (!fused_mc) {
+  if (sizeof(T) == 2 && n <= MC_SMALL_MAX_PAIRS && !getenv("UAHN_NO_MC_SMALL_FUSED")) {
+    // latency path: dropout expansion + first layer of both heads in ONE CUDA-core kernel (was expand + 2 launches)
+    h->prof_begin(2);
+    LAUNCH(launch_mc_fc1_small_fused(n, feat, h->W1m_plain, h->W1u_plain, h->b1m, h->b1u, h->hid, d_masks, seed, first, rng_dev, st));
+    h->prof_end();
+  } else if (!fused_mc) {
     h->prof_begin(3);
     LAUNCH(launch_mc_expand<T>(n, feat, (T*)h->mcA, d_masks, seed, first, rng_dev, st));
     h->prof_end();

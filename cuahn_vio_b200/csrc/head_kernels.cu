@@ -113,6 +113,7 @@ __global__ void dlt_kernel(int n, const float* __restrict__ off, const float* __
 // FC8_PAIRS pairs per CTA so each 8x5120 weight read from L2 is shared by 4 feature vectors.
 // feat is the last conv output in NHWC order ((h*5+w)*256 + c); W8 was permuted to that order at load.
 constexpr int FC8_PAIRS = 4;
+constexpr int FC8_SMALL_MAX = 8;   // up to here: fc8_dlt_cluster_kernel (split-K over a cluster)
 template <typename T>
 __global__ void __launch_bounds__(256) fc8_dlt_kernel(int n, const T* __restrict__ feat, const float* __restrict__ W8,
                                                        const float* __restrict__ b8, const float* __restrict__ Hprev,
@@ -168,6 +169,94 @@ __global__ void __launch_bounds__(256) fc8_dlt_kernel(int n, const T* __restrict
       corner(i, x, y);
       dst[2 * i] = __fadd_rn(x, d_s[wid][2 * i]);
       dst[2 * i + 1] = __fadd_rn(y, d_s[wid][2 * i + 1]);
+    }
+    double h[9];
+    dlt_warp(dst, h);
+    if (lane == 0) {
+      float hb[9], out[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) hb[i] = (float)h[i];
+      if (Hprev) {
+        float hp[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) hp[i] = Hprev[pair * 9 + i];
+        mat3_mul(hp, hb, out);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) out[i] = hb[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Hout[pair * 9 + i] = out[i];
+    }
+  }
+}
+
+// Latency path (<= FC8_SMALL_MAX pairs): the same stage with the 5120-long dot products split over a cluster of 8 CTAs per
+// pair (640 k each, 8 x fewer dependent L2 round trips per thread), partial sums reduced through distributed shared
+// memory into rank 0, which adds the bias and runs the DLT + composition.  (One CTA per 4 pairs takes 20 us at batch 1.)
+constexpr int FC8_CLUSTER = 8;
+template <typename T>
+__global__ void __cluster_dims__(FC8_CLUSTER, 1, 1) __launch_bounds__(256)
+    fc8_dlt_cluster_kernel(int n, const T* __restrict__ feat, const float* __restrict__ W8, const float* __restrict__ b8,
+                           const float* __restrict__ Hprev, float* __restrict__ Hout, float* __restrict__ dout) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float part[8][8];
+  __shared__ float red[FC8_CLUSTER][8];     // rank 0's copy collects every rank's partial sums
+  __shared__ float d_s[8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x / FC8_CLUSTER;
+  constexpr int KPER = FC_IN / FC8_CLUSTER;   // 640
+  const int k0 = (int)rank * KPER;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+#pragma unroll
+  for (int i = 0; i < (KPER + 255) / 256; ++i) {
+    const int kk = tid + 256 * i;
+    if (kk < KPER) {
+      const int k = k0 + kk;
+      const float x = to_f32<T>(feat[(size_t)pair * FC_IN + k]);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = fmaf(x, __ldg(W8 + o * FC_IN + k), acc[o]);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sft);
+    if (lane == 0) part[wid][o] = acc[o];
+  }
+  __syncthreads();
+  if (tid < 8) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += part[w][tid];
+    // red[rank][tid] in the shared memory of cluster rank 0
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&red[rank][tid])), "r"(0u));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+  }
+  cluster_sync_all();                        // release / acquire: the remote stores are visible to rank 0
+  if (rank != 0) return;
+  if (tid < 8) {
+    float v = 0.f;
+#pragma unroll
+    for (int c = 0; c < FC8_CLUSTER; ++c) v += red[c][tid];
+    v += b8[tid];
+    d_s[tid] = v;
+    if (dout) dout[pair * 8 + tid] = v;
+  }
+  __syncthreads();
+  if (wid == 0) {                            // one warp: DLT + composition
+    float dst[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x, y;
+      corner(i, x, y);
+      dst[2 * i] = __fadd_rn(x, d_s[2 * i]);
+      dst[2 * i + 1] = __fadd_rn(y, d_s[2 * i + 1]);
     }
     double h[9];
     dlt_warp(dst, h);
@@ -295,6 +384,105 @@ __global__ void __launch_bounds__(256) mc_fc1_small_kernel(const __nv_bfloat16* 
 #pragma unroll
     for (int w = 0; w < 8; ++w) { v0 += part[w][s][jp]; v1 += part[w][s][jp + 1]; }
     reinterpret_cast<uint32_t*>(out + ((size_t)pair * MC + s) * FC_HID + j0 + jp)[0] = pack_lrelu_bf16x2(v0, v1);
+  }
+}
+
+// The same layer with the MC-dropout expansion fused in and both heads in one launch (the latency path's 3 launches ->
+// 1): every CTA first builds the keep bytes of its (pair, head) in shared memory — [k8][sample], bit j = keep(8*k8 + j),
+// from the Philox generator or the explicit masks, exactly the bytes mc_maskbits_kernel / mc_expand_kernel use — then runs
+// the dot products on feat directly: a = keep ? bf16(feat * 1/0.95) : 0, the value mc_expand_kernel would have stored.
+__global__ void __launch_bounds__(256) mc_fc1_small_fused_kernel(const __nv_bfloat16* __restrict__ feat, int n,
+                                                                  const __nv_bfloat16* __restrict__ Wm,
+                                                                  const __nv_bfloat16* __restrict__ Wu,
+                                                                  const float* __restrict__ bm, const float* __restrict__ bu,
+                                                                  __nv_bfloat16* __restrict__ hid,
+                                                                  const uint8_t* __restrict__ keep_masks, uint64_t seed,
+                                                                  uint64_t first_pair, const uint64_t* __restrict__ rng_dev) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }
+  __shared__ float part[8][MC][FC1S_JT];
+  __shared__ __align__(16) uint8_t s_bits[(FC_IN / 8) * MC];      // 10 KB
+  __shared__ uint32_t s_tab[256];
+  const int j0 = blockIdx.x * FC1S_JT, pair = blockIdx.y, head = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (keep_masks) {
+    for (int i = tid; i < MC * (FC_IN / 8); i += 256) {
+      const int k8 = i / MC, smp = i - k8 * MC;
+      const uint8_t* m = keep_masks + ((size_t)(pair * 2 + head) * MC + smp) * MASK_ROW;
+      uint32_t bits = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kp = k8 * 8 + j, hw = kp >> 8, c = kp & 255;   // kernel order -> reference order c*20 + hw
+        bits |= (m[c * 20 + hw] ? 1u : 0u) << j;
+      }
+      s_bits[i] = (uint8_t)bits;
+    }
+  } else {
+    s_tab[tid] = g_keep_alias[tid];
+    __syncthreads();
+#pragma unroll 2
+    for (int i = tid; i < MC * (FC_IN / 32); i += 256) {
+      const int k32 = i / MC, smp = i - k32 * MC;
+      uint32_t b[4];
+      philox_keep32(seed, first_pair + pair, head, 0, smp, k32, s_tab, b);
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) s_bits[(k32 * 4 + qd) * MC + smp] = (uint8_t)b[qd];
+    }
+  }
+  __syncthreads();
+  const uint4* f4 = reinterpret_cast<const uint4*>(feat + (size_t)pair * FC_IN);
+  const uint4* w4 = reinterpret_cast<const uint4*>((head ? Wu : Wm) + (size_t)j0 * FC_IN);
+  float acc[MC][FC1S_JT];
+#pragma unroll
+  for (int s_ = 0; s_ < MC; ++s_)
+#pragma unroll
+    for (int j = 0; j < FC1S_JT; ++j) acc[s_][j] = 0.f;
+  auto lo = [](uint32_t v) { return __uint_as_float(v << 16); };
+  auto hi = [](uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); };
+  for (int g = tid; g < FC_IN / 8; g += 256) {
+    float wf[FC1S_JT][8];
+#pragma unroll
+    for (int j = 0; j < FC1S_JT; ++j) {
+      const uint4 w = __ldg(w4 + (size_t)j * (FC_IN / 8) + g);
+      wf[j][0] = lo(w.x); wf[j][1] = hi(w.x); wf[j][2] = lo(w.y); wf[j][3] = hi(w.y);
+      wf[j][4] = lo(w.z); wf[j][5] = hi(w.z); wf[j][6] = lo(w.w); wf[j][7] = hi(w.w);
+    }
+    const uint4 fv = __ldg(f4 + g);
+    const float fr[8] = {lo(fv.x), hi(fv.x), lo(fv.y), hi(fv.y), lo(fv.z), hi(fv.z), lo(fv.w), hi(fv.w)};
+    float kept[8];                                     // the bf16 value mc_expand_kernel stores for a kept unit
+#pragma unroll
+    for (int e = 0; e < 8; ++e) kept[e] = __bfloat162float(__float2bfloat16_rn(__fmul_rn(fr[e], KEEP_SCALE)));
+    const uint4 bw = *reinterpret_cast<const uint4*>(s_bits + g * MC);   // this granule's keep bytes of the 16 samples
+    const uint32_t bword[4] = {bw.x, bw.y, bw.z, bw.w};
+#pragma unroll
+    for (int s_ = 0; s_ < MC; ++s_) {
+      const uint32_t bits = (bword[s_ >> 2] >> (8 * (s_ & 3))) & 0xFFu;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float a = (bits >> e) & 1u ? kept[e] : 0.f;
+#pragma unroll
+        for (int j = 0; j < FC1S_JT; ++j) acc[s_][j] = fmaf(a, wf[j][e], acc[s_][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int s_ = 0; s_ < MC; ++s_)
+#pragma unroll
+    for (int j = 0; j < FC1S_JT; ++j) {
+      float v = acc[s_][j];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) part[wid][s_][j] = v;
+    }
+  __syncthreads();
+  if (tid < MC * FC1S_JT / 2) {            // one thread per pair of adjacent output columns
+    const int s_ = tid / (FC1S_JT / 2), jp = (tid % (FC1S_JT / 2)) * 2;
+    const float* bias = head ? bu : bm;
+    float v0 = bias[j0 + jp], v1 = bias[j0 + jp + 1];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { v0 += part[w][s_][jp]; v1 += part[w][s_][jp + 1]; }
+    __nv_bfloat16* out = hid + (size_t)head * n * MC * FC_HID;
+    reinterpret_cast<uint32_t*>(out + ((size_t)pair * MC + s_) * FC_HID + j0 + jp)[0] = pack_lrelu_bf16x2(v0, v1);
   }
 }
 
@@ -521,6 +709,8 @@ cudaError_t launch_dlt(int n, const float* off, const float* Hprev, float* Hout,
 template <typename T>
 cudaError_t launch_fc8_dlt(int n, const T* feat, const float* W8, const float* b8, const float* Hprev, float* Hout,
                            float* dout, cudaStream_t st) {
+  if (n <= FC8_SMALL_MAX)   // latency path: a cluster of 8 CTAs per pair (compile-time cluster dimensions)
+    return launch_pdl(fc8_dlt_cluster_kernel<T>, dim3(FC8_CLUSTER * n), dim3(256), 0, st, n, feat, W8, b8, Hprev, Hout, dout);
   return launch_pdl(fc8_dlt_kernel<T>, dim3((n + FC8_PAIRS - 1) / FC8_PAIRS), dim3(256), 0, st, n, feat, W8, b8, Hprev, Hout, dout);
 }
 template cudaError_t launch_fc8_dlt<float>(int, const float*, const float*, const float*, const float*, float*, float*,
@@ -541,6 +731,14 @@ template cudaError_t launch_mc_expand<__nv_bfloat16>(int, const __nv_bfloat16*, 
 cudaError_t launch_mc_fc1_small(int n, const void* A, const void* W, const float* bias, void* out, cudaStream_t st) {
   return launch_pdl(mc_fc1_small_kernel, dim3(FC_HID / FC1S_JT, n), dim3(256), 0, st, (const __nv_bfloat16*)A,
                     (const __nv_bfloat16*)W, bias, (__nv_bfloat16*)out);
+}
+
+cudaError_t launch_mc_fc1_small_fused(int n, const void* feat, const void* Wm, const void* Wu, const float* bm, const float* bu,
+                                      void* hid, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,
+                                      const uint64_t* rng_dev, cudaStream_t st) {
+  return launch_pdl(mc_fc1_small_fused_kernel, dim3(FC_HID / FC1S_JT, n, 2), dim3(256), 0, st, (const __nv_bfloat16*)feat, n,
+                    (const __nv_bfloat16*)Wm, (const __nv_bfloat16*)Wu, bm, bu, (__nv_bfloat16*)hid, keep_masks, seed,
+                    first_pair, rng_dev);
 }
 
 // host side: build the alias table and upload it to the current device (idempotent; called by uahn_create)

@@ -35,6 +35,10 @@ cudaError_t launch_mc_expand(int n, const T* feat, T* A, const uint8_t* keep_mas
                              const uint64_t* rng_dev, cudaStream_t st);
 // first MC-head layer on CUDA cores for the batch-1 latency path (bf16): A [n][16][5120], W [256][5120], out [n][16][256]
 cudaError_t launch_mc_fc1_small(int n, const void* A, const void* W, const float* bias, void* out, cudaStream_t st);
+// the same with the dropout expansion fused in and both heads in one launch: feat [n][5120] bf16 -> hid [2][n][16][256]
+cudaError_t launch_mc_fc1_small_fused(int n, const void* feat, const void* Wm, const void* Wu, const float* bm, const float* bu,
+                                      void* hid, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,
+                                      const uint64_t* rng_dev, cudaStream_t st);
 // bits[head][pair][k8][sample]: keep bits of the first MC dropout for the fused masked GEMM (bf16 path)
 cudaError_t init_keep_alias_table();   // uploads the keep-byte alias table (common.cuh) to the current device
 cudaError_t launch_mc_maskbits(int n, uint8_t* bits, const uint8_t* keep_masks, uint64_t seed, uint64_t first_pair,

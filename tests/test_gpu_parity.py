@@ -218,10 +218,34 @@ def test_fused_mc_gemm_matches_expand_path(api, wfile):
         m_big, c_big, _ = net.infer_batch(prev, curr, prior, seed=5, first_pair=100)          # fused, Philox bits
         m_exp, c_exp, _ = net.infer_batch(prev, curr, prior, keep_masks=packed)               # fused, explicit masks
         assert np.array_equal(m_big, m_exp) and np.array_equal(c_big, c_exp)
-        for lo in (0, 32, 64):                                                                # expand path, 6 pairs at a time
-            m6, c6, _ = net.infer_batch(prev[lo:lo + 6], curr[lo:lo + 6], prior[lo:lo + 6], seed=5, first_pair=100 + lo)
-            assert np.abs(m6 - m_big[lo:lo + 6]).max() < 2e-3, np.abs(m6 - m_big[lo:lo + 6]).max()
-            assert np.abs(c6 - c_big[lo:lo + 6]).max() <= 2e-3 * np.abs(c6).max()
+        # expand + plain GEMM path, 12 pairs at a time (9..63 pairs: above the latency-path kernels, whose split-K FC8 sums in
+        # another order and would move the cascade by bf16 flips; below the fused MC GEMM)
+        for lo in (0, 32, 58):
+            m6, c6, _ = net.infer_batch(prev[lo:lo + 12], curr[lo:lo + 12], prior[lo:lo + 12], seed=5, first_pair=100 + lo)
+            assert np.abs(m6 - m_big[lo:lo + 12]).max() < 2e-3, np.abs(m6 - m_big[lo:lo + 12]).max()
+            assert np.abs(c6 - c_big[lo:lo + 12]).max() <= 2e-3 * np.abs(c6).max()
+
+
+def test_latency_path_mc_kernel_is_the_expand_path_bit_for_bit(api, wfile):
+    """<= 8 pairs, bf16: dropout expansion + first MC-head layer of both heads in one CUDA-core kernel vs the three launches
+    it replaces (mc_expand + 2 x mc_fc1_small): the same bf16 values in the same summation order."""
+    import os
+    n = 5
+    prev, curr, _, prior = S.synthetic_batch(n, start=1200)
+    packed = np.stack([api.philox_keep_masks(21, 300 + i) for i in range(n)])
+    res = {}
+    for fused in (True, False):
+        if not fused:
+            os.environ["UAHN_NO_MC_SMALL_FUSED"] = "1"
+        try:
+            with api.Uahn(wfile, "prior3", precision="bf16", max_batch=n) as net:
+                res[fused] = (net.infer_batch(prev, curr, prior, seed=21, first_pair=300)[:2],
+                              net.infer_batch(prev, curr, prior, keep_masks=packed)[:2])
+        finally:
+            os.environ.pop("UAHN_NO_MC_SMALL_FUSED", None)
+    for a, b in zip(res[True], res[False]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(res[True][0][0], res[True][1][0])           # Philox == the same masks replayed explicitly
 
 
 def test_sequence_submission_matches_pairwise_call(api, wfile):
