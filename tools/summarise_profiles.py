@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn the raw ncu outputs of one profiled step into the tracked summaries under profiles/.
 
-    python tools/summarise_profiles.py gpurun_out/launches_final3.csv /tmp/step_full.csv [bench.json]
+    python tools/summarise_profiles.py gpurun_out/launches.csv /tmp/step_full.csv [bench.json] [--round r02] [--pairs 1024]
 
 The first argument is the launch list (`ncu --metrics gpu__time_duration.sum --csv --log-file …`), the second the
 `ncu -i prof.ncu-rep --page raw --csv` dump of the `--set full` capture of the same command.  Both hold the 25 launches
@@ -51,15 +51,28 @@ def launches(path):
 
 
 def main():
+    argv = list(sys.argv)
+    rnd, pairs = "r02", 1024
+    for flag in ("--round", "--pairs"):
+        if flag in argv:
+            i = argv.index(flag)
+            val = argv[i + 1]
+            del argv[i:i + 2]
+            if flag == "--round":
+                rnd = val
+            else:
+                pairs = int(val)
+    sys.argv = argv
+    DESC = ("CTA-pair fused block fronts (2-row Toeplitz conv 1, N = 128; 64-byte-row input planes), TMA shifted-window + "
+            "im2col-TMA igemm convs, fused MC GEMM, fast-coordinate warp")
     lpath, fpath = sys.argv[1], sys.argv[2]
     ls = launches(lpath)
     assert len(ls) == len(STAGES), (len(ls), len(STAGES))
     total = sum(x[3] for x in ls)
-    with open(os.path.join(ROOT, "profiles", "r01_launches_step_b1024.csv"), "w") as f:
-        f.write("# ncu launch list — one 3-block UAHN step, 1024 pairs, bf16 (round 1, final kernels: CTA-pair fused block "
-                "fronts, TMA shifted-window + im2col-TMA igemm convs, fused MC GEMM)\n")
+    with open(os.path.join(ROOT, "profiles", f"{rnd}_launches_step_b{pairs}.csv"), "w") as f:
+        f.write(f"# ncu launch list — one 3-block UAHN step, {pairs} pairs, bf16 ({rnd}, final kernels: {DESC})\n")
         f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 25 -c 25 --csv python "
-                "tools/profile_step.py --batch 1024 --steps 2\n")
+                f"tools/profile_step.py --batch {pairs} --steps 2\n")
         f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
         f.write("stage,kernel,grid,block,time_us,share\n")
         for s, (k, g, b, t) in zip(STAGES, ls):
@@ -75,9 +88,9 @@ def main():
     assert len(data) == len(STAGES), len(data)
     idx = {k: hdr.index(k) for k in FULL_KEYS}
     conv_bytes = 0.0
-    with open(os.path.join(ROOT, "profiles", "r01_ncu_step_full_b1024.csv"), "w") as f:
+    with open(os.path.join(ROOT, "profiles", f"{rnd}_ncu_step_full_b{pairs}.csv"), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on -s 25 -c 25 python tools/profile_step.py --batch "
-                "1024 --steps 2  (round 1, final kernels; one 3-block step, 1024 pairs, bf16)\n")
+                f"{pairs} --steps 2  ({rnd}, final kernels; one 3-block step, {pairs} pairs, bf16)\n")
         f.write("# per-launch values are cold-cache and serialised: compare SHARES, not absolutes.  Units: us, MB, MB, % of "
                 "peak x3, MB (L2->SM), then % of peak\n")
         f.write("stage,kernel," + ",".join(FULL_KEYS) + "\n")
@@ -95,12 +108,13 @@ def main():
                     conv_bytes += x * 1e6
             f.write(f'{s},"{short(r[hdr.index("Kernel Name")])}",' + ",".join(vals) + "\n")
     n_conv = sum(1 for s in STAGES if s.startswith("block"))
-    json.dump({"pairs": 1024, "conv_group_dram_bytes_per_step": conv_bytes, "conv_launches": n_conv,
-               "source": "profiles/r01_ncu_step_full_b1024.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum "
+    tname = f"{rnd}_conv_traffic.json" if pairs == 1024 else f"{rnd}_conv_traffic_b{pairs}.json"
+    json.dump({"pairs": pairs, "conv_group_dram_bytes_per_step": conv_bytes, "conv_launches": n_conv,
+               "source": f"profiles/{rnd}_ncu_step_full_b{pairs}.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum "
                          f"over the {n_conv} conv launches of one step)"},
-              open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json"), "w"))
+              open(os.path.join(ROOT, "profiles", tname), "w"))
     if len(sys.argv) > 3:
-        shutil.copy(sys.argv[3], os.path.join(ROOT, "profiles", "r01_bench_bf16.json"))
+        shutil.copy(sys.argv[3], os.path.join(ROOT, "profiles", f"{rnd}_bench_bf16.json"))
     print("launch total %.1f us, conv dram %.1f MB" % (total, conv_bytes / 1e6))
 
 
