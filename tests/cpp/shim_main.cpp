@@ -1,6 +1,8 @@
 // Host program exercising the C++ drop-in class (include/HomographyNet.h) the way VioManager does
 // (VioManager.cpp:107,188,236,257-259): ctor, load_current_img per frame, network_inference, getters.
-// usage: shim_main <weights.bin> <frames.u8 (k x 224 x 320)> <k> <priors.f64 (k x 8)> <precision>
+// usage: shim_main <weights.bin> <frames.u8 (k x 224 x 320)> <k> <priors.f64 (k x 8)> <precision> [<iterative weights.bin>]
+// With an iterative model (max_IEKF_iteration = 2) every frame also runs iteration 1 on the second model slot
+// (HomographyNet.cpp:209-230) and prints its outputs as ITER lines.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -19,7 +21,8 @@ int main(int argc, char** argv) {
   f = fopen(argv[4], "rb");
   if (!f || fread(priors.data(), 8, priors.size(), f) != priors.size()) return 3;
   fclose(f);
-  pytorch::HomographyNet net(model, iter_model, /*use_prior=*/true, /*num_of_iteration=*/1, /*show_imgs=*/false,
+  if (argc > 6) iter_model = argv[6];
+  pytorch::HomographyNet net(model, iter_model, /*use_prior=*/true, /*num_of_iteration=*/argc > 6 ? 2 : 1, /*show_imgs=*/false,
                              atoi(argv[5]));
   net.set_seed(9);
   for (int i = 0; i < k; ++i) {
@@ -29,6 +32,12 @@ int main(int argc, char** argv) {
     for (int j = 0; j < 8; ++j) printf(" %.9g", net.pred_mean()[j]);
     for (int j = 0; j < 8; ++j) printf(" %.9g", net.pred_cov()[j * 9]);
     printf("\n");
+    if (argc > 6 && net.img_counter >= 2) {
+      net.network_inference(priors.data() + (size_t)i * 8, 1);
+      printf("ITER %d", i);
+      for (int j = 0; j < 8; ++j) printf(" %.9g", net.pred_mean()[j]);
+      printf("\n");
+    }
   }
   return 0;
 }

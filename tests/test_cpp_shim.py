@@ -57,3 +57,37 @@ def test_reference_signature_flavour_type_checks():
            os.path.join(ROOT, "tests", "cpp", "shim_reference_signatures.cpp")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.gpu
+def test_shim_iterative_slot_runs_the_graph_the_file_holds(tmp_path):
+    """HomographyNet.cpp:104-124,209-230: the second model slot runs whatever graph its file holds.  A flat file exported
+    from a TorchScript trace records the variant (weights.export_torchscript); here the records are written directly for a
+    1-block and a 2-block iterative model, and the shim's iteration 1 must equal a PRIOR1 / PRIOR2 handle."""
+    from cuahn_vio_b200 import api, synthetic as S, weights
+    exe = _compile(tmp_path)
+    wfile = weights.synthetic_weights_file(0)
+    sd = S.synthetic_state_dict(0)
+    prev, curr, _, prior = S.synthetic_batch(1, start=41)
+    frames = np.stack([prev[0], curr[0]])
+    pri = np.stack([prior[0], prior[0]]).reshape(2, 8).astype(np.float64)
+    frames.tofile(tmp_path / "frames.u8")
+    pri.tofile(tmp_path / "priors.f64")
+    for variant in ("prior1", "prior2"):
+        it_file = str(tmp_path / f"iter_{variant}.bin")
+        weights.export_state_dict(sd, it_file, meta={"variant": weights.VARIANT_IDS[variant], "show_error": 0})
+        out = subprocess.run([exe, wfile, str(tmp_path / "frames.u8"), "2", str(tmp_path / "priors.f64"), "0", it_file],
+                             check=True, capture_output=True, text=True).stdout
+        it = [l.split() for l in out.splitlines() if l.startswith("ITER")]
+        assert len(it) == 1
+        with api.Uahn(wfile, variant, precision="fp32", max_batch=1) as net:
+            # the shim numbers its forwards 0, 1, ...: main model = pair index 0, iteration 1 = pair index 1 (seed 9)
+            m, _, _ = net.infer_batch(frames[0:1], frames[1:2], pri[1:2].astype(np.float32), seed=9, first_pair=1)
+        assert np.allclose(np.array(it[0][2:10], float), m[0], atol=1e-6), variant
+    # a file without a record falls back to the 2-block schedule (and says nothing alarming)
+    out = subprocess.run([exe, wfile, str(tmp_path / "frames.u8"), "2", str(tmp_path / "priors.f64"), "0", wfile],
+                         check=True, capture_output=True, text=True)
+    it = [l.split() for l in out.stdout.splitlines() if l.startswith("ITER")]
+    with api.Uahn(wfile, "prior2", precision="fp32", max_batch=1) as net:
+        m, _, _ = net.infer_batch(frames[0:1], frames[1:2], pri[1:2].astype(np.float32), seed=9, first_pair=1)
+    assert np.allclose(np.array(it[0][2:10], float), m[0], atol=1e-6)
