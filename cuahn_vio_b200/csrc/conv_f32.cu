@@ -3,6 +3,8 @@
 // 5-10x margin over fp32 noise).  M = output pixels of the whole batch, N = Cout, K = KH*KW*Cin.
 // Inputs/outputs are zero-haloed NHWC fp32 tensors, so the k-th im2col element of a pixel is simply
 // in[row_base(pixel) + koff(k)] with no bounds test.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -16,7 +18,7 @@ template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(CONV_THREADS) conv_f32_kernel(const float* __restrict__ in,
                                                                 const float* __restrict__ wk,  // [K][Cout]
                                                                 const float* __restrict__ bias, float* __restrict__ out,
-                                                                ConvGeom g) {
+                                                                ConvGeom g, float* __restrict__ ws, int k_per_split) {
   static_assert((BM / TM) * (BN / TN) == CONV_THREADS, "thread tiling");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* As = reinterpret_cast<float*>(smem_raw);              // [BK][BM]
@@ -48,16 +50,19 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_f32_kernel(const float* __r
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < g.K; k0 += BK) {
+  // split-K (ws != nullptr): blockIdx.z owns K range [z * k_per_split, (z + 1) * k_per_split) and writes raw partial sums
+  // to ws[z][M][Cout]; splitk_reduce_kernel adds them in a fixed order, then bias + activation
+  const int k_lo = ws ? blockIdx.z * k_per_split : 0, k_hi = ws ? min(g.K, k_lo + k_per_split) : g.K;
+  for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
     for (int idx = tid; idx < BM * BK; idx += CONV_THREADS) {
       const int m = idx % BM, kk = idx / BM;
       const int k = k0 + kk;
-      As[kk * BM + m] = (k < g.K) ? __ldg(in + rowbase[m] + koff[k]) : 0.f;
+      As[kk * BM + m] = (k < k_hi) ? __ldg(in + rowbase[m] + koff[k]) : 0.f;
     }
     for (int idx = tid; idx < BN * BK; idx += CONV_THREADS) {
       const int nn = idx % BN, kk = idx / BN;
       const int k = k0 + kk;
-      Bs[kk * BN + nn] = (k < g.K && n0 + nn < g.Cout) ? __ldg(wk + (size_t)k * g.Cout + n0 + nn) : 0.f;
+      Bs[kk * BN + nn] = (k < k_hi && n0 + nn < g.Cout) ? __ldg(wk + (size_t)k * g.Cout + n0 + nn) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -79,6 +84,15 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_f32_kernel(const float* __r
   for (int i = 0; i < TM; ++i) {
     const int gm = m0 + ty * TM + i;
     if (gm >= g.M) continue;
+    if (ws) {
+      float* w = ws + ((size_t)blockIdx.z * g.M + gm) * g.Cout;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int c = n0 + tx * TN + j;
+        if (c < g.Cout) w[c] = acc[i][j];
+      }
+      continue;
+    }
     const int n = gm / hw, r = gm - n * hw;
     const int oy = r / g.Wo, ox = r - oy * g.Wo;
     float* o = out + g.out_origin + (long long)n * g.out_pitch_n + (long long)oy * g.out_pitch_y +
@@ -94,26 +108,64 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_f32_kernel(const float* __r
   }
 }
 
+thread_local int g_extra_launches = 0;   // kernels beyond the first that the last launch_conv_f32 call enqueued (launch accounting)
+
+// out[pixel][c] = act(sum_z ws[z][pixel][c] + bias[c]), z ascending: deterministic whatever the grid
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
+                                                             float* __restrict__ out, ConvGeom g, int splits) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.M * g.Cout) return;
+  const int gm = idx / g.Cout, c = idx - gm * g.Cout;
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += ws[((size_t)z * g.M + gm) * g.Cout + c];
+  v += bias ? __ldg(bias + c) : 0.f;
+  const int hw = g.Ho * g.Wo, n = gm / hw, r = gm - n * hw, oy = r / g.Wo, ox = r - oy * g.Wo;
+  out[g.out_origin + (long long)n * g.out_pitch_n + (long long)oy * g.out_pitch_y + (long long)ox * g.Cout + c] =
+      g.act ? lrelu(v) : v;
+}
+
 template <int BM, int BN, int TM, int TN>
 cudaError_t launch_cfg(const float* in, const float* wk, const float* bias, float* out, const ConvGeom& g,
-                       cudaStream_t st) {
+                       cudaStream_t st, float* ws = nullptr, size_t ws_floats = 0, int rows_per_pair = 0) {
   const size_t smem = (size_t)(BK * BM + BK * BN) * 4 + (size_t)BM * 8 + (size_t)g.K * 4;
   static SmemOptIn optin;   // per device (common.cuh)
   if (smem > 48 * 1024)
     if (cudaError_t e = optin.ensure(conv_f32_kernel<BM, BN, TM, TN>, smem); e != cudaSuccess) return e;
   dim3 grid((g.M + BM - 1) / BM, (g.Cout + BN - 1) / BN);
-  conv_f32_kernel<BM, BN, TM, TN><<<grid, CONV_THREADS, smem, st>>>(in, wk, bias, out, g);
+  // Latency path: a deep layer at one or a few pairs is a handful of CTAs walking a long K loop (256 -> 256: 4 CTAs x 144
+  // k-chunks, 474 us at batch 1).  Split K over the idle SMs; partial sums meet in a workspace and are added in a fixed
+  // order, so the result does not depend on the split's scheduling.
+  // The split depends on the LAYER only (the tile count of ONE pair), never on the batch: every pair of a small batch is
+  // summed in the order it would be summed in alone, so "a batch is a loop of batch-1 forwards" stays bit-exact.
+  const int tiles1 = (rows_per_pair + BM - 1) / BM * (int)grid.y, k_chunks = (g.K + BK - 1) / BK, num_sms = device_num_sms();
+  int splits = 1;
+  if (ws && rows_per_pair > 0 && tiles1 * 2 <= num_sms && k_chunks >= 8)
+    splits = std::min(std::min(num_sms / tiles1, k_chunks / 2), 64);
+  if (splits > 1 && (size_t)splits * g.M * g.Cout <= ws_floats) {
+    const int k_per_split = (k_chunks + splits - 1) / splits * BK;
+    grid.z = (g.K + k_per_split - 1) / k_per_split;
+    conv_f32_kernel<BM, BN, TM, TN><<<grid, CONV_THREADS, smem, st>>>(in, wk, bias, out, g, ws, k_per_split);
+    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) return e;
+    const int total = g.M * g.Cout;
+    splitk_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, bias, out, g, (int)grid.z);
+    g_extra_launches = 1;
+    return cudaGetLastError();
+  }
+  conv_f32_kernel<BM, BN, TM, TN><<<grid, CONV_THREADS, smem, st>>>(in, wk, bias, out, g, nullptr, 0);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t launch_conv_f32(const float* in, const float* wk, const float* bias, float* out, const ConvGeom& g,
-                            cudaStream_t st) {
-  if (g.Cout >= 64) return launch_cfg<64, 64, 4, 4>(in, wk, bias, out, g, st);
+                            cudaStream_t st, float* ws, size_t ws_floats, int rows_per_pair) {
+  g_extra_launches = 0;
+  if (g.Cout >= 64) return launch_cfg<64, 64, 4, 4>(in, wk, bias, out, g, st, ws, ws_floats, rows_per_pair);
   if (g.Cout >= 32) return launch_cfg<128, 32, 4, 4>(in, wk, bias, out, g, st);
   if (g.Cout >= 16) return launch_cfg<256, 16, 4, 4>(in, wk, bias, out, g, st);
   return launch_cfg<256, 8, 4, 2>(in, wk, bias, out, g, st);
 }
+
+int conv_f32_extra_launches() { return g_extra_launches; }
 
 }  // namespace uahn

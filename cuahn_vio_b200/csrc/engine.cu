@@ -89,6 +89,7 @@ const LayerSpec B1[] = {{"block_1_1", 128, 2, 7, 2}, {"block_1_2", 128, 128, 5, 
 const LayerSpec B2[] = {{"block_2_1", 64, 2, 7, 2}, {"block_2_2", 128, 64, 5, 2}, {"block_2_3", 256, 128, 3, 2}, {"block_2_4", 256, 256, 3, 2}};
 const LayerSpec B3[] = {{"block_3_0", 16, 2, 7, 1}, {"block_3_1", 32, 16, 5, 2}, {"block_3_2", 64, 32, 3, 2}, {"block_3_3", 128, 64, 3, 2}, {"block_3_4", 256, 128, 3, 2}, {"block_3_5", 256, 256, 3, 2}};
 const LayerSpec B4[] = {{"block_4_0", 8, 2, 7, 1}, {"block_4_1", 16, 8, 5, 2}, {"block_4_2", 32, 16, 3, 2}, {"block_4_3", 64, 32, 3, 2}, {"block_4_4", 128, 64, 3, 2}, {"block_4_5", 256, 128, 3, 2}, {"block_4_6", 256, 256, 3, 2}};
+constexpr int F32_SPLITK_MAX_PAIRS = 8; // fp32: up to here the deep SIMT layers split K over the idle SMs (latency path)
 constexpr int MC_SMALL_MAX_PAIRS = 8;    // bf16: up to here the first MC-head layer runs on CUDA cores (latency path)
 constexpr int MC_FUSED_MIN_PAIRS = 64;   // bf16: batches from this size on use the fused masked-A MC GEMM
 const char* P1 = "model_part1.";
@@ -138,6 +139,8 @@ struct uahn_handle {
   void* hid = nullptr;    // [2][cap][16][256] T
   float* Hb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // cumulative H after prior(0)/block1..3 ; [4] unused
   float* Htot = nullptr;
+  float* f32_ws = nullptr;        // fp32 mode: split-K workspace of the SIMT convolutions (latency path)
+  size_t f32_ws_floats = 0;
   float* dblk[4] = {nullptr, nullptr, nullptr, nullptr};          // regressed offsets of blocks 1..3
   float *mc_mean = nullptr, *mc_logvar = nullptr;
   // staging for the host-pointer entry points
@@ -412,7 +415,9 @@ int run_conv(uahn_handle* h, Layer& L, int n, size_t out_img0 = 0) {
   ConvGeom g = make_geom(L, n);
   T* out = (T*)L.out.p + out_img0 * (size_t)L.out.pitch_n;     // first output image (chunked block fronts)
   if constexpr (sizeof(T) == 4) {
-    LAUNCH(launch_conv_f32((const float*)L.in.p, L.w_f32, L.bias, (float*)out, g, h->stream));
+    LAUNCH(launch_conv_f32((const float*)L.in.p, L.w_f32, L.bias, (float*)out, g, h->stream, n <= F32_SPLITK_MAX_PAIRS ? h->f32_ws : nullptr,
+                           h->f32_ws_floats, L.Ho * L.Wo));
+    h->launches += conv_f32_extra_launches();
   } else {
     LAUNCH(launch_conv_bf16(L.wb, L.in.p, L.bias, out, g, h->stream));
   }
@@ -509,7 +514,9 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
       const T* a = (const T*)h->mcA + (size_t)head * n * MC * FC_IN;
       T* o = (T*)h->hid + (size_t)head * n * MC * FC_HID;
       if constexpr (sizeof(T) == 4) {
-        LAUNCH(launch_conv_f32((const float*)a, head ? h->W1u : h->W1m, head ? h->b1u : h->b1m, (float*)o, g, st));
+        LAUNCH(launch_conv_f32((const float*)a, head ? h->W1u : h->W1m, head ? h->b1u : h->b1m, (float*)o, g, st,
+                               n <= F32_SPLITK_MAX_PAIRS ? h->f32_ws : nullptr, h->f32_ws_floats, MC));
+        h->launches += conv_f32_extra_launches();
       } else if (n <= MC_SMALL_MAX_PAIRS) {     // latency path: CUDA-core kernel, 64 CTAs per pair and head
         LAUNCH(launch_mc_fc1_small(n, a, head ? h->W1u_plain : h->W1m_plain, head ? h->b1u : h->b1m, o, st));
       } else {
@@ -650,6 +657,10 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
     if ((rc = dev_alloc(h, &h->dblk[i], cap * 8))) return bail(rc);
   }
   if ((rc = dev_alloc(h, &h->Htot, cap * 9))) return bail(rc);
+  if (!h->bf16) {   // splits * M * Cout <= num_sms * 64 * 64 * pairs by construction (conv_f32.cu)
+    h->f32_ws_floats = (size_t)h->num_sms * 64 * 64 * F32_SPLITK_MAX_PAIRS;
+    if ((rc = dev_alloc(h, &h->f32_ws, h->f32_ws_floats, false))) return bail(rc);
+  }
   if ((rc = dev_alloc(h, &h->mc_mean, cap * MC * 8))) return bail(rc);
   if ((rc = dev_alloc(h, &h->mc_logvar, cap * MC * 8))) return bail(rc);
   if ((rc = dev_alloc(h, &h->d_prev, cap * IMG_PIXELS))) return bail(rc);

@@ -19,8 +19,11 @@ cudaError_t launch_remap_u8(const uint8_t* raw, int rows, int cols, const float*
                             cudaStream_t st);
 
 // conv_f32.cu
+// ws: optional split-K workspace (ws_floats floats) for the small-M deep layers of the latency path; rows_per_pair: GEMM rows
+// one pair contributes (Ho * Wo, or 16 for the MC-head linears) — the split is chosen from it, not from the batch
 cudaError_t launch_conv_f32(const float* in, const float* wk, const float* bias, float* out, const ConvGeom& g,
-                            cudaStream_t st);
+                            cudaStream_t st, float* ws = nullptr, size_t ws_floats = 0, int rows_per_pair = 0);
+int conv_f32_extra_launches();   // kernels beyond the first that this thread's last launch_conv_f32 call enqueued (split-K reduce)
 
 // head_kernels.cu
 // transfer_mean_var_single + packing for n pairs: var, pts_w [n][8], Hp [n][9] -> flow [n][8], cov [n][64]
