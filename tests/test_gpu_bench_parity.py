@@ -274,3 +274,27 @@ def test_fast_coordinate_path_indices_bit_exact_over_18M_coordinates(api, wfile,
         mism += int((ix[t][inside] != rix[inside]).sum() + (iy[t][inside] != riy[inside]).sum())
         checked += 2 * int(inside.sum())
     assert mism == 0 and checked > 30_000_000, (mism, checked)
+
+
+def test_every_kernel_selection_boundary_vs_oracle(api, wfile, synth_sd):
+    """Kernel selection switches with the batch size (latency-path kernels <= 8 pairs, expand-path MC head 9..63, fused MC
+    GEMM from 64, CTA-pair MC GEMM from 256, CTA-pair deep layers once a layer has a tile per SM): first, middle and last
+    pair of a call on both sides of every switch, bf16 vs the oracle."""
+    sizes = (1, 2, 8, 9, 63, 64, 65, 255, 256, 257, 1023)
+    uniq = 24
+    prev, curr, _, prior = S.synthetic_batch(uniq, start=5000)
+    oracle_cache = {}
+    worst_px = worst_cov = 0.0
+    with api.Uahn(wfile, "prior3", precision="bf16", max_batch=max(sizes)) as net:
+        for n in sizes:
+            idx = np.arange(n) % uniq
+            seed, first = 600 + n, 10 * n
+            m, c, _ = net.infer_batch(prev[idx], curr[idx], prior[idx], seed=seed, first_pair=first)
+            assert np.isfinite(m).all() and np.isfinite(c).all(), n
+            pick = sorted({0, n // 2, n - 1})
+            masks = [philox_masks_for_oracle(api, seed, first + i) for i in pick]
+            sel = idx[pick]
+            om, oc, _ = O.forward_batch(prev[sel], curr[sel], synth_sd, masks, prior[sel], False)
+            px, rel = check_pairs(m[pick], c[pick], om, oc, f"n={n}")
+            worst_px, worst_cov = max(worst_px, px), max(worst_cov, rel)
+    print(f"\n[parity] bf16 prior3 at batch sizes {sizes}: max |offset| err {worst_px:.4f} px, max cov rel err {worst_cov:.4f}")
