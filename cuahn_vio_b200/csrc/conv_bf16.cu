@@ -630,6 +630,13 @@ int conv_bf16_prepare(ConvBf16Weights& wb, const std::vector<float>& wk, const s
                       const ConvGeom& g, const Tensor& in, const Tensor& out, std::vector<void*>& allocs,
                       std::string& err) {
   (void)out;
+  if (in.p) {   // block_2_1: the dedicated TMA-staged stride-2 first-layer kernel
+    std::string serr;
+    const int rc = conv_s2first_prepare(wb.s2, wk, bias, g, in, allocs, serr);
+    if (rc < 0) { err = serr; return rc; }
+    // (the gather operands below are still built: they serve batches whose last tile the TMA path does not cover — none
+    //  today — and UAHN_NO_S2FIRST A/B runs)
+  }
   if (in.p && !getenv("UAHN_NO_TMA")) {
     std::string terr;
     const int rc = conv_tma_prepare(wb.tma, wk, bias, g, in, allocs, terr);
@@ -773,6 +780,7 @@ cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const fl
                              const ConvGeom& g, cudaStream_t st) {
   if (!wb.ready) return cudaErrorInvalidValue;
   const int num_sms = device_num_sms();
+  if (wb.s2.enabled) return launch_conv_s2first(wb.s2, out, g, num_sms, st);
   if (wb.tma.enabled) return launch_conv_tma(wb.tma, bias, out, g, num_sms, st);
   IgemmParams p{};
   const int xb = wb.xb;

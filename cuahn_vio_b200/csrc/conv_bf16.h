@@ -35,8 +35,21 @@ int conv_fused_prepare(FusedPlan& plan, const std::vector<float>& wk0, const std
 cudaError_t launch_conv_fused(const FusedPlan& plan, void* out, const ConvGeom& g1, int n_img, int num_sms,
                               cudaStream_t st);
 
+// block_2_1 (conv_s2_first.cu): 7x7 stride-2 conv of the 2-channel block input, TMA-staged, N = 128.
+struct S2Plan {
+  int enabled = 0;
+  alignas(64) unsigned char tmap[128];
+  int TX = 0, TY = 0, Ho = 0, Wog = 0;
+  void* b_image = nullptr;
+  float* bias_x = nullptr;
+};
+int conv_s2first_prepare(S2Plan& plan, const std::vector<float>& wk, const std::vector<float>& bias, const ConvGeom& g,
+                         const Tensor& x, std::vector<void*>& allocs, std::string& err);
+cudaError_t launch_conv_s2first(const S2Plan& plan, void* out, const ConvGeom& g, int num_sms, cudaStream_t st);
+
 struct ConvBf16Weights {
   TmaPlan tma;
+  S2Plan s2;
   void* b_image = nullptr;   // pre-swizzled B-operand stages in global memory
   int ready = 0;
   int xb = 1;                // output pixels per GEMM row (Toeplitz expansion along x)
