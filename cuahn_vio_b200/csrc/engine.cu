@@ -162,9 +162,13 @@ struct uahn_handle {
   // (ring slot, explicit masks?, error map?) combination, captured on the second call and replayed afterwards
   cudaGraphExec_t graphs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t graph_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  uint64_t* d_rng = nullptr;    // {seed, first_pair} read by the MC kernels during graph replay
-  uint64_t* h_rng = nullptr;    // pinned
-  float* h_prior = nullptr;     // pinned 8 floats
+  // batch-1 inputs travel as ONE 48-byte H2D copy and the results as ONE 288-byte D2H copy (every copy is a graph node
+  // of its own on the latency path): {seed, first_pair, prior[8]} pinned + device, {mean[8], cov[64]} device
+  uint64_t* d_rng = nullptr;    // device block: {seed, first_pair} read by the MC kernels during graph replay, then prior[8]
+  uint64_t* h_rng = nullptr;    // pinned block, same layout
+  float* h_prior = nullptr;     // = (float*)(h_rng + 2)
+  float* d_in1_prior = nullptr; // = (float*)(d_rng + 2)
+  float* d_out1 = nullptr;      // device {mean[8], cov[64]} of uahn_infer
   uint64_t infer_calls = 0;
   bool use_graph = true;
   // pairs per chunk of the block-3/4 fronts (UAHN_L2_CHUNK).  Measured on B200 at 1024 pairs/step: chunks of
@@ -670,15 +674,17 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
   if ((rc = dev_alloc(h, &h->d_cov, cap * 64))) return bail(rc);
   if (h->cfg.show_error && (rc = dev_alloc(h, &h->d_err, cap * IMG_PIXELS))) return bail(rc);
   if ((rc = dev_alloc(h, &h->d_ring, (size_t)2 * IMG_PIXELS))) return bail(rc);
-  if ((rc = dev_alloc(h, &h->d_rng, 2))) return bail(rc);
+  if ((rc = dev_alloc(h, &h->d_rng, 2 + 4))) return bail(rc);
+  h->d_in1_prior = reinterpret_cast<float*>(h->d_rng + 2);
+  if ((rc = dev_alloc(h, &h->d_out1, 72))) return bail(rc);
   h->use_graph = getenv("UAHN_NO_GRAPH") == nullptr;
-  if ((e = cudaMallocHost((void**)&h->h_rng, 16)) != cudaSuccess ||
-      (e = cudaMallocHost((void**)&h->h_prior, 32)) != cudaSuccess ||
+  if ((e = cudaMallocHost((void**)&h->h_rng, 48)) != cudaSuccess ||
       (e = cudaMallocHost((void**)&h->h_img, IMG_PIXELS)) != cudaSuccess ||
       (e = cudaMallocHost((void**)&h->h_out, (72 + IMG_PIXELS) * sizeof(float))) != cudaSuccess) {
     h->fail(UAHN_ERR_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e));
     return bail(UAHN_ERR_CUDA);
   }
+  h->h_prior = reinterpret_cast<float*>(h->h_rng + 2);
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) {
     h->fail(UAHN_ERR_CUDA, "setup: %s", cudaGetErrorString(e));
     return bail(UAHN_ERR_CUDA);
@@ -697,7 +703,6 @@ void uahn_destroy(uahn_handle* h) {
   for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
   for (cudaGraphExec_t g : h->graphs) if (g) cudaGraphExecDestroy(g);
   if (h->h_rng) cudaFreeHost(h->h_rng);
-  if (h->h_prior) cudaFreeHost(h->h_prior);
   if (h->h_img) cudaFreeHost(h->h_img);
   if (h->h_raw) cudaFreeHost(h->h_raw);
   if (h->h_out) cudaFreeHost(h->h_out);
@@ -884,15 +889,13 @@ int uahn_infer(uahn_handle* h, const double* prior_px, const uahn_rng* rng, doub
   const uint8_t* prev = h->d_ring + (size_t)(h->ring_curr ^ 1) * IMG_PIXELS;
   // everything between the host buffers: prior + rng H2D, the forward, results D2H
   auto enqueue = [&]() -> int {
-    if (need_prior) CK(cudaMemcpyAsync(h->d_prior, h->h_prior, 32, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_rng, h->h_rng, 16, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_rng, h->h_rng, need_prior ? 48 : 16, cudaMemcpyHostToDevice, st));
     // the error map leaves the device already clamped and truncated to u8 (HomographyNet.cpp:201): 71 680 B of D2H
     // instead of 286 720 B of floats plus a host conversion loop
-    int rc = forward_any(h, 1, prev, curr, need_prior ? h->d_prior : nullptr, rng, dm, h->d_mean, h->d_cov, nullptr,
+    int rc = forward_any(h, 1, prev, curr, need_prior ? h->d_in1_prior : nullptr, rng, dm, h->d_out1, h->d_out1 + 8, nullptr,
                          h->d_rng, err_map ? reinterpret_cast<uint8_t*>(h->d_err) : nullptr);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->h_out, h->d_mean, 8 * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h->h_out + 8, h->d_cov, 64 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_out, h->d_out1, 72 * 4, cudaMemcpyDeviceToHost, st));
     if (err_map) CK(cudaMemcpyAsync(h->h_out + 72, h->d_err, (size_t)IMG_PIXELS, cudaMemcpyDeviceToHost, st));
     return UAHN_OK;
   };
