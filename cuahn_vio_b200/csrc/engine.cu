@@ -90,6 +90,7 @@ const LayerSpec B2[] = {{"block_2_1", 64, 2, 7, 2}, {"block_2_2", 128, 64, 5, 2}
 const LayerSpec B3[] = {{"block_3_0", 16, 2, 7, 1}, {"block_3_1", 32, 16, 5, 2}, {"block_3_2", 64, 32, 3, 2}, {"block_3_3", 128, 64, 3, 2}, {"block_3_4", 256, 128, 3, 2}, {"block_3_5", 256, 256, 3, 2}};
 const LayerSpec B4[] = {{"block_4_0", 8, 2, 7, 1}, {"block_4_1", 16, 8, 5, 2}, {"block_4_2", 32, 16, 3, 2}, {"block_4_3", 64, 32, 3, 2}, {"block_4_4", 128, 64, 3, 2}, {"block_4_5", 256, 128, 3, 2}, {"block_4_6", 256, 256, 3, 2}};
 constexpr int F32_SPLITK_MAX_PAIRS = 8; // fp32: up to here the deep SIMT layers split K over the idle SMs (latency path)
+constexpr int WARP_TEX_MIN_PAIRS = 8;    // bf16: above this the warp takes its taps by texture gather (image_kernels.cu SMALL_BATCH)
 constexpr int MC_SMALL_MAX_PAIRS = 8;    // bf16: up to here the first MC-head layer runs on CUDA cores (latency path)
 constexpr int MC_FUSED_MIN_PAIRS = 64;   // bf16: batches from this size on use the fused masked-A MC GEMM
 const char* P1 = "model_part1.";
@@ -145,6 +146,7 @@ struct uahn_handle {
   float *mc_mean = nullptr, *mc_logvar = nullptr;
   // staging for the host-pointer entry points
   uint8_t *d_prev = nullptr, *d_curr = nullptr, *d_masks = nullptr;
+  WarpCells cells;          // bf16, batches above the latency path: the current frames as a texture-gather array (image_kernels.cu)
   float *d_prior = nullptr, *d_mean = nullptr, *d_cov = nullptr, *d_err = nullptr;
   // streaming (load_image / infer) state: 2-slot ring
   uint8_t* d_ring = nullptr;
@@ -430,7 +432,8 @@ int run_conv(uahn_handle* h, Layer& L, int n, size_t out_img0 = 0) {
 
 // warp + concat + pool -> conv stack of one cascade block.  The front (warp, conv 0, conv 1) runs per L2-sized chunk.
 template <typename T>
-int run_block(uahn_handle* h, Block& B, int n, const uint8_t* prev, const uint8_t* curr, const float* Hcur) {
+int run_block(uahn_handle* h, Block& B, int n, const uint8_t* prev, const uint8_t* curr, const float* Hcur,
+              const WarpCells* cells = nullptr) {
   cudaStream_t st = h->stream;
   int rc;
   const int CH = B.chunk_cap;
@@ -439,7 +442,7 @@ int run_block(uahn_handle* h, Block& B, int n, const uint8_t* prev, const uint8_
     if constexpr (sizeof(T) == 2) {
       const int num_sms = h->num_sms;
       h->prof_begin(0);
-      LAUNCH(launch_warp_concat_pool<T>(prev, curr, Hcur, B.x, B.pool, n, st));
+      LAUNCH(launch_warp_concat_pool<T>(prev, curr, Hcur, B.x, B.pool, n, st, cells));
       h->prof_end();
       h->prof_begin(1);
       LAUNCH(launch_conv_fused(B.fused, B.layers[1].out.p, make_geom(B.layers[1], n), n, num_sms, st));
@@ -453,7 +456,7 @@ int run_block(uahn_handle* h, Block& B, int n, const uint8_t* prev, const uint8_
     const int nc = std::min(CH, n - c0);
     h->prof_begin(0);
     LAUNCH(launch_warp_concat_pool<T>(prev + (size_t)c0 * IMG_PIXELS, curr + (size_t)c0 * IMG_PIXELS,
-                                      Hcur ? Hcur + (size_t)c0 * 9 : nullptr, B.x, B.pool, nc, st));
+                                      Hcur ? Hcur + (size_t)c0 * 9 : nullptr, B.x, B.pool, nc, st, CH >= n ? cells : nullptr));
     h->prof_end();
     h->prof_begin(1);
     if ((rc = run_conv<T>(h, B.layers[0], nc))) return rc;
@@ -483,11 +486,20 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
     h->prof_end();
     Hcur = h->Hb[0];
   }
+  // bf16, above the latency path: the warps gather their taps through the texture unit from a cell array of the current
+  // frames (image_kernels.cu), filled here once per call; charged to the warp stage
+  const WarpCells* cells = nullptr;
+  if (sizeof(T) == 2 && h->cells.arr && n > WARP_TEX_MIN_PAIRS && n <= h->cells.cap) {
+    h->prof_begin(0);
+    LAUNCH(launch_warp_cells_fill(h->cells, curr, n, st));
+    h->prof_end();
+    cells = &h->cells;
+  }
   for (int b = 1; b <= 3; ++b) {
     Block& B = h->blocks[b];
     if (!B.active) continue;
     // block 1 sees the raw current image (model_to_trace.py:138-139); blocks 2,3 the warped one (:154,172)
-    if ((rc = run_block<T>(h, B, n, prev, curr, b == 1 ? nullptr : Hcur))) return rc;
+    if ((rc = run_block<T>(h, B, n, prev, curr, b == 1 ? nullptr : Hcur, cells))) return rc;
     h->prof_begin(3);
     LAUNCH(launch_fc8_dlt<T>(n, (const T*)B.layers.back().out.p, B.W8, B.b8, b == 1 ? nullptr : Hcur, h->Hb[b],
                              h->dblk[b], st));
@@ -495,7 +507,7 @@ int forward(uahn_handle* h, int n, const uint8_t* prev, const uint8_t* curr, con
     Hcur = h->Hb[b];
   }
   Block& B4 = h->blocks[4];
-  if ((rc = run_block<T>(h, B4, n, prev, curr, Hcur))) return rc;             // model_to_trace.py:261-263
+  if ((rc = run_block<T>(h, B4, n, prev, curr, Hcur, cells))) return rc;      // model_to_trace.py:261-263
   const T* feat = (const T*)B4.layers.back().out.p;
   const uint64_t seed = rng ? rng->seed : 0, first = rng ? rng->first_pair_index : 0;
   // bf16, large batches: the dropout expansion is fused into the GEMM's A producer and only the keep BITS (20 KB per
@@ -669,6 +681,12 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
   if ((rc = dev_alloc(h, &h->mc_logvar, cap * MC * 8))) return bail(rc);
   if ((rc = dev_alloc(h, &h->d_prev, cap * IMG_PIXELS))) return bail(rc);
   if ((rc = dev_alloc(h, &h->d_curr, cap * IMG_PIXELS))) return bail(rc);
+  if (h->bf16 && h->cap > WARP_TEX_MIN_PAIRS && h->cap <= warp_cells_capacity() && !getenv("UAHN_NO_TEX_WARP")) {
+    if ((e = warp_cells_create(h->cells, h->cap, h->stream)) != cudaSuccess) {
+      h->fail(UAHN_ERR_CUDA, "cell array of the texture-gather warp (%d images): %s", h->cap, cudaGetErrorString(e));
+      return bail(UAHN_ERR_CUDA);
+    }
+  }
   if ((rc = dev_alloc(h, &h->d_prior, cap * 8))) return bail(rc);
   if ((rc = dev_alloc(h, &h->d_mean, cap * 8))) return bail(rc);
   if ((rc = dev_alloc(h, &h->d_cov, cap * 64))) return bail(rc);
@@ -697,6 +715,7 @@ void uahn_destroy(uahn_handle* h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  warp_cells_destroy(h->cells);
   for (auto& sp : h->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }

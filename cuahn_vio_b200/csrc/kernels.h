@@ -5,9 +5,22 @@
 namespace uahn {
 
 // image_kernels.cu
+// The current frames of one call as zero-separated cells of a 2-D CUDA array: the source of the texture-gather warp kernel
+// (bf16 path, batches above the latency path).  fill: linear u8 frames [n][224][320] -> cells.
+struct WarpCells {
+  cudaArray_t arr = nullptr;
+  cudaTextureObject_t tex = 0;
+  cudaSurfaceObject_t surf = 0;
+  int cap = 0;
+};
+int warp_cells_capacity();      // images one array can hold (texture-gather arrays are limited to 32768 x 32768 texels)
+cudaError_t warp_cells_create(WarpCells& c, int cap, cudaStream_t st);
+void warp_cells_destroy(WarpCells& c);
+cudaError_t launch_warp_cells_fill(const WarpCells& c, const uint8_t* frames, int n, cudaStream_t st);
+// cells != nullptr (bf16 only): curr has been copied into the cell array by launch_warp_cells_fill
 template <typename T>
 cudaError_t launch_warp_concat_pool(const uint8_t* prev, const uint8_t* curr, const float* Hmat, const Tensor& out,
-                                    int pool, int n, cudaStream_t st);
+                                    int pool, int n, cudaStream_t st, const WarpCells* cells = nullptr);
 // out (float) or out_u8 (error map clamped to [0,255] and truncated, HomographyNet.cpp:201) — exactly one is non-null
 // allow_fast: the bf16 product path's coordinate mode (image_kernels.cu CM_FAST: fast coordinates, exact fallback near
 // integer boundaries — indices stay bit-exact); 0 = the exact chain everywhere (fp32 validation mode)
