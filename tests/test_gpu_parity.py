@@ -402,6 +402,45 @@ def test_fused_front_matches_per_layer_kernels(api, wfile):
     assert np.abs(outs[True][0] - outs[False][0]).max() < BF16_PX
 
 
+def test_texture_warp_matches_shared_memory_warp(api, wfile):
+    """bf16, more than 8 pairs: the texture-gather warp kernel (taps by tld4 from the cell array) against the shared-memory
+    kernel on the same inputs — identity (every sample on the integer grid: exact chain), far-outside and partly-outside
+    homographies (clamp into the zero margin) and ordinary ones; all three pooling factors."""
+    import os
+    n = 12
+    prev, curr, _, prior = S.synthetic_batch(n, start=640)
+    prior = prior.copy()
+    prior[0] = 0.0                                   # identity
+    prior[1] = 400.0                                 # every sample outside the image
+    prior[2] = np.array([[-30, -25], [28, -31], [-27, 30], [31, 26]], np.float32)    # zoom: all four borders leave the image
+    prior[3, :, 0] += 21.0                           # pure shift: the left border samples the zero padding
+    outs = {}
+    # True: the default (only the unpooled launch uses phased strips); "all": phased strips in all three launches
+    for tex, env in ((True, None), ("all", "UAHN_STRIP_PHASE_ALL"), (False, "UAHN_NO_TEX_WARP")):
+        if env:
+            os.environ[env] = "1"
+        try:
+            with api.Uahn(wfile, "prior3", precision="bf16", max_batch=n) as net:
+                m, c, _ = net.infer_batch(prev, curr, prior, seed=4)
+                outs[tex] = (m, c, net.debug_read("x2", (n, 2, 56, 80)), net.debug_read("x3", (n, 2, 112, 160)),
+                             net.debug_read("x4", (n, 2, 224, 320)))
+        finally:
+            if env:
+                os.environ.pop(env, None)
+    for k in range(5):                                         # the strip phase only changes which thread owns a pixel
+        assert np.array_equal(outs[True][k], outs["all"][k])
+    # x2 sees the same H in both runs: the two kernels may differ by the rounding of a tap sum (b / 255 per tap against
+    # one scaling of the integer sum), i.e. by one bf16 ulp in a few pixels.  x3 / x4 follow H2 / H3, which those flips move
+    # by ~1e-3 px.
+    for k, max_frac in ((2, 0.02), (3, 0.3), (4, 0.3)):
+        a, b = outs[True][k], outs[False][k]
+        assert np.array_equal(a[:, 0], b[:, 0])                # previous-frame channel: exact integer sums in both
+        assert np.abs(a - b).max() <= 2.0 ** -8                # one bf16 ulp below 1.0
+        assert np.mean(a != b) < max_frac
+    assert np.abs(outs[True][2][1, 1]).max() == 0.0            # far outside: zeros
+    assert np.abs(outs[True][0] - outs[False][0]).max() < BF16_PX
+
+
 def test_cta_pair_deep_layers_match_single_cta_kernels(api, wfile):
     """Deep conv layers (Cin % 64 == 0) at a batch large enough for the CTA-pair kernels (tcgen05.mma.cta_group::2, half
     of each B stage per CTA) vs the one-CTA im2col kernels: the same accumulation order, so every activation and output

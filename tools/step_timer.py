@@ -42,5 +42,12 @@ for r in range(a.rounds):
     e1.record()
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) / 20)
-prof = net.profile() if hasattr(net, "profile") else None
-print(a.tag, "ms/step:", " ".join("%.4f" % t for t in ts), prof or "")
+# stage split of the same steady state (per-stage CUDA events: warp / conv / MC GEMM / small kernels)
+net.profile_enable(True)
+for _ in range(20):
+    step()
+net.synchronize()
+ms, cnt = net.profile_read()
+net.profile_enable(False)
+print(a.tag, "ms/step:", " ".join("%.4f" % t for t in ts), "| stages ms/step (warp, conv, mc gemm, small):",
+      " ".join("%.4f" % (m / 20) for m in ms))
