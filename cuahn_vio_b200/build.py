@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libuahn.so")
-SOURCES = ["engine.cu", "image_kernels.cu", "conv_f32.cu", "conv_bf16.cu", "conv_bf16_tma.cu", "conv_fused_front.cu", "conv_s2_first.cu", "head_kernels.cu", "ekf_update.cpp", "preproc_maps.cpp", "imu_propagate.cpp"]
+SOURCES = ["engine.cu", "image_kernels.cu", "conv_f32.cu", "conv_bf16.cu", "conv_bf16_tma.cu", "conv_fused_front.cu", "conv_s2_first.cu", "conv_small_m.cu", "head_kernels.cu", "ekf_update.cpp", "preproc_maps.cpp", "imu_propagate.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-cudart", "static"]

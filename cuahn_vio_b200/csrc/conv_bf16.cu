@@ -782,6 +782,7 @@ cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const fl
   const int num_sms = device_num_sms();
   if (wb.s2.enabled) return launch_conv_s2first(wb.s2, out, g, num_sms, st);
   if (wb.tma.enabled) return launch_conv_tma(wb.tma, bias, out, g, num_sms, st);
+  if (conv_small_m_ok(wb, g)) return launch_conv_small_m(wb, in, wb.bias_x, out, g, st);   // batch 1-2: split-K over a cluster
   IgemmParams p{};
   const int xb = wb.xb;
   p.in = (const uint8_t*)in;

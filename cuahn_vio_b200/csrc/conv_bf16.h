@@ -81,5 +81,9 @@ cudaError_t launch_mc_gemm_bf16(const ConvBf16Weights& wb, const void* feat, con
                                 cudaStream_t st);
 cudaError_t launch_conv_bf16(const ConvBf16Weights& wb, const void* in, const float* bias, void* out,
                              const ConvGeom& g, cudaStream_t st);
+// conv_small_m.cu — latency path (M <= 160 GEMM rows, Cin % 64 == 0): split-K over a cluster of 8 CTAs, mma.sync
+int conv_small_m_ok(const ConvBf16Weights& wb, const ConvGeom& g);
+cudaError_t launch_conv_small_m(const ConvBf16Weights& wb, const void* in, const float* bias, void* out, const ConvGeom& g,
+                                cudaStream_t st);
 
 }  // namespace uahn

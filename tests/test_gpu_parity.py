@@ -375,6 +375,37 @@ def test_conv_layers_vs_torch(api, wfile, synth_sd, precision):
             assert err < tol, (name, precision, err, scale)
 
 
+SMALL_M_LAYERS = [  # the layers the latency path runs as split-K over a cluster (conv_small_m.cu): M = 20 or 70 rows per pair
+    ("block_1_2", 128, 14, 20, 128, 5, 2), ("block_1_3", 128, 7, 10, 256, 3, 2), ("block_2_3", 128, 14, 20, 256, 3, 2),
+    ("block_2_4", 256, 7, 10, 256, 3, 2), ("block_3_4", 128, 14, 20, 256, 3, 2), ("block_3_5", 256, 7, 10, 256, 3, 2),
+    ("block_4_5", 128, 14, 20, 256, 3, 2), ("block_4_6", 256, 7, 10, 256, 3, 2),
+]
+
+
+def test_small_m_split_k_layers_vs_torch_and_batch_independent(api, wfile, synth_sd):
+    """bf16 latency path: every deep layer by name at 1 and 2 pairs (and 8 for the 4x5 layers) against torch fp64 on the
+    bf16-rounded operands; a 2-pair call is bit for bit two 1-pair calls (the K split never depends on the batch)."""
+    g = torch.Generator().manual_seed(11)
+    with api.Uahn(wfile, "full", precision="bf16", max_batch=8) as net:
+        for name, cin, hin, win, cout, k, s in SMALL_M_LAYERS:
+            pre = "model_last_block_list.0." if name.startswith("block_4") else "model_part1."
+            w, b = _bf16_round(synth_sd[pre + name + ".0.weight"]), synth_sd[pre + name + ".0.bias"]
+            ho, wo = (hin + 2 * ((k - 1) // 2) - k) // s + 1, (win + 2 * ((k - 1) // 2) - k) // s + 1
+            for n in (1, 2, 8):
+                x = _bf16_round(torch.rand(n, cin, hin, win, generator=g) * 2 - 0.5)
+                ref = torch.nn.functional.leaky_relu(
+                    torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=s, padding=(k - 1) // 2), 0.1).float()
+                l0 = net.launch_count
+                out = net.stage_conv(name, x.numpy(), (cout, ho, wo))
+                assert net.launch_count - l0 == 1
+                scale = max(1.0, float(ref.abs().max()))
+                assert np.abs(out - ref.numpy()).max() < 6e-3 * scale, (name, n)
+                if n == 2:
+                    for i in range(2):
+                        one = net.stage_conv(name, x[i:i + 1].numpy(), (cout, ho, wo))
+                        assert np.array_equal(one[0], out[i]), (name, i)
+
+
 def test_fused_front_matches_per_layer_kernels(api, wfile):
     """Blocks 3/4: the fused conv0+conv1 kernel vs the two separate tcgen05 kernels (same bf16 intermediate)."""
     import os

@@ -4,8 +4,8 @@
     python tools/summarise_profiles.py gpurun_out/launches.csv /tmp/step_full.csv [bench.json] [--round r02] [--pairs 1024]
 
 The first argument is the launch list (`ncu --metrics gpu__time_duration.sum --csv --log-file …`), the second the
-`ncu -i prof.ncu-rep --page raw --csv` dump of the `--set full` capture of the same command.  Both hold the 25 launches
-of one 3-block step at 1024 pairs (tools/profile_step.py --batch 1024 --steps 2, -s 25 -c 25).
+`ncu -i prof.ncu-rep --page raw --csv` dump of the `--set full` capture of the same command.  Both hold the 26 launches
+of one 3-block step at 1024 pairs (tools/profile_step.py --batch 1024 --steps 2, -s 26 -c 26).
 """
 import csv
 import json
@@ -14,7 +14,7 @@ import shutil
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STAGES = ["dlt(prior)", "warp+pool4 (block 2 input)", "block_2_1", "block_2_2", "block_2_3", "block_2_4", "fc8+dlt (block 2)",
+STAGES = ["dlt(prior)", "warp cells fill (current frames -> texture-gather array)", "warp+pool4 (block 2 input)", "block_2_1", "block_2_2", "block_2_3", "block_2_4", "fc8+dlt (block 2)",
           "warp+pool2 (block 3 input)", "block_3 front: conv7x7+conv5x5s2 fused (CTA pairs)", "block_3_2", "block_3_3",
           "block_3_4", "block_3_5", "fc8+dlt (block 3)", "warp (block 4 input)",
           "block_4 front: conv7x7+conv5x5s2 fused (CTA pairs)", "block_4_2", "block_4_3", "block_4_4", "block_4_5",
@@ -64,14 +64,14 @@ def main():
                 pairs = int(val)
     sys.argv = argv
     DESC = ("CTA-pair fused block fronts (2-row Toeplitz conv 1, N = 128; 64-byte-row input planes), TMA shifted-window + "
-            "im2col-TMA igemm convs, fused MC GEMM, fast-coordinate warp")
+            "im2col-TMA igemm convs, fused MC GEMM, texture-gather warp")
     lpath, fpath = sys.argv[1], sys.argv[2]
     ls = launches(lpath)
     assert len(ls) == len(STAGES), (len(ls), len(STAGES))
     total = sum(x[3] for x in ls)
     with open(os.path.join(ROOT, "profiles", f"{rnd}_launches_step_b{pairs}.csv"), "w") as f:
         f.write(f"# ncu launch list — one 3-block UAHN step, {pairs} pairs, bf16 ({rnd}, final kernels: {DESC})\n")
-        f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 25 -c 25 --csv python "
+        f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 26 -c 26 --csv python "
                 f"tools/profile_step.py --batch {pairs} --steps 2\n")
         f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
         f.write("stage,kernel,grid,block,time_us,share\n")
@@ -89,7 +89,7 @@ def main():
     idx = {k: hdr.index(k) for k in FULL_KEYS}
     conv_bytes = 0.0
     with open(os.path.join(ROOT, "profiles", f"{rnd}_ncu_step_full_b{pairs}.csv"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -s 25 -c 25 python tools/profile_step.py --batch "
+        f.write("# ncu --set full --clock-control none --import-source on -s 26 -c 26 python tools/profile_step.py --batch "
                 f"{pairs} --steps 2  ({rnd}, final kernels; one 3-block step, {pairs} pairs, bf16)\n")
         f.write("# per-launch values are cold-cache and serialised: compare SHARES, not absolutes.  Units: us, MB, MB, % of "
                 "peak x3, MB (L2->SM), then % of peak\n")
