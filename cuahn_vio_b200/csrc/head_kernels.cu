@@ -5,6 +5,8 @@
 //   * MC-dropout expansion of the block-4 feature (model_to_trace.py:222-235,272-273)
 //   * second head layer, 16-sample ensemble (model_to_trace.py:274-281), covariance transfer
 //     (model_to_trace.py:18-38), output packing and the showError homography (model_to_trace.py:311-323)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_ptx.cuh"
@@ -19,7 +21,9 @@ __device__ __forceinline__ void corner(int i, float& x, float& y) {   // model_t
 
 // All 32 lanes call with the same `dst` (4 destination points, fp32 like the reference's `pts0 + d`).
 // Lane r (mod 8) owns row r of the 8x9 augmented system; result h[0..8] (h[8] = 1) on every lane.
-__device__ void dlt_warp(const float* dst, double* h) {
+// The general solver: Gauss-Jordan with partial pivoting by warp shuffles.  Since the latency work of round 2 the product path
+// takes dlt_rect below (the system always has the same four source points); UAHN_DLT_ELIMINATION=1 switches back.
+__device__ void dlt_elimination_warp(const float* dst, double* h) {
   const int lane = threadIdx.x & 31, r = lane & 7, pt = r >> 1;
   float sx, sy;
   corner(pt, sx, sy);
@@ -64,6 +68,33 @@ __device__ void dlt_warp(const float* dst, double* h) {
     h[c] = __shfl_sync(0xffffffffu, xr, owner);
   }
   h[8] = 1.0;
+}
+
+// The same solve in closed form.  The four source points are always the corners of the 320 x 224 frame
+// (model_to_trace.py:78-83), so the 8x8 system is the square-to-quadrilateral mapping (Heckbert, "Fundamentals of Texture
+// Mapping and Image Warping", 1989, sec. 2.2.3) composed with the frame's scaling: with (u, v) = (x / (W-1), y / (H-1)) and
+// the unit square's corners (0,0), (1,0), (1,1), (0,1) going to q0, q1, q2, q3,
+//   g = | S  d2 | / | d1 d2 |,  h = | d1 S | / | d1 d2 |   (d1 = q1 - q2, d2 = q3 - q2, S = q0 - q1 + q2 - q3),
+//   X = (a u + b v + c) / (g u + h v + 1) with a = q1.x - q0.x + g q1.x, b = q3.x - q0.x + h q3.x, c = q0.x (Y alike).
+// ~40 fp64 operations per lane and no shuffles instead of eight dependent elimination steps (~3 us of every DLT launch on the
+// batch-1 chain).  Same exact solution: in fp64 the two agree to ~1e-12, far inside the fp32 noise of the reference's
+// torch.inverse (tests/test_gpu_parity.py::test_stage_dlt_matches_reference runs both).
+__device__ __forceinline__ void dlt_rect(const float* dst, double* h) {
+  // corner order of the model: UL, BL, BR, UR  ->  q0 = UL, q1 = UR, q2 = BR, q3 = BL
+  const double x0 = dst[0], y0 = dst[1], x3 = dst[2], y3 = dst[3], x2 = dst[4], y2 = dst[5], x1 = dst[6], y1 = dst[7];
+  const double dx1 = x1 - x2, dx2 = x3 - x2, dy1 = y1 - y2, dy2 = y3 - y2;
+  const double sx = (x0 - x1) + (x2 - x3), sy = (y0 - y1) + (y2 - y3);
+  const double inv = 1.0 / (dx1 * dy2 - dy1 * dx2);
+  const double g = (sx * dy2 - sy * dx2) * inv, k = (dx1 * sy - dy1 * sx) * inv;
+  constexpr double IW = 1.0 / (IMG_W - 1), IH = 1.0 / (IMG_H - 1);
+  h[0] = ((x1 - x0) + g * x1) * IW; h[1] = ((x3 - x0) + k * x3) * IH; h[2] = x0;
+  h[3] = ((y1 - y0) + g * y1) * IW; h[4] = ((y3 - y0) + k * y3) * IH; h[5] = y0;
+  h[6] = g * IW; h[7] = k * IH; h[8] = 1.0;
+}
+__constant__ int c_dlt_elimination;      // 1: the warp-shuffle elimination (set once per process from UAHN_DLT_ELIMINATION)
+__device__ __forceinline__ void dlt_warp(const float* dst, double* h) {
+  if (c_dlt_elimination) dlt_elimination_warp(dst, h);
+  else dlt_rect(dst, h);
 }
 
 // fp32 3x3 product, k accumulated sequentially with FMA (torch.bmm on CPU)
@@ -743,6 +774,8 @@ cudaError_t launch_mc_fc1_small_fused(int n, const void* feat, const void* Wm, c
 
 // host side: build the alias table and upload it to the current device (idempotent; called by uahn_create)
 cudaError_t init_keep_alias_table() {
+  const int elim = getenv("UAHN_DLT_ELIMINATION") != nullptr;   // (rides along: both are per-device constants set at create)
+  if (cudaError_t e = cudaMemcpyToSymbol(c_dlt_elimination, &elim, sizeof(elim)); e != cudaSuccess) return e;
   uint32_t tab[256];
   build_keep_alias_table(tab);
   return cudaMemcpyToSymbol(g_keep_alias, tab, sizeof(tab));

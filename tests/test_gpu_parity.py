@@ -44,8 +44,23 @@ def _oracle_batch(prev, curr, sd, masks_list, priors, show_error, btr=3):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def test_stage_dlt_matches_reference(api, wfile, golden_stages):
+@pytest.mark.parametrize("solver", ["closed form", "elimination"])
+def test_stage_dlt_matches_reference(api, wfile, golden_stages, solver):
+    """Both DLT solvers of head_kernels.cu: the closed form of the fixed source rectangle (product path) and the
+    warp-shuffle Gauss-Jordan elimination (UAHN_DLT_ELIMINATION=1)."""
+    import os
     g = golden_stages
+    if solver == "elimination":
+        os.environ["UAHN_DLT_ELIMINATION"] = "1"
+    try:
+        _check_stage_dlt(api, wfile, g)
+    finally:
+        os.environ.pop("UAHN_DLT_ELIMINATION", None)
+        with api.Uahn(wfile, "prior1", max_batch=1):      # the solver switch is a per-process device constant: restore it
+            pass
+
+
+def _check_stage_dlt(api, wfile, g):
     with api.Uahn(wfile, "prior1", max_batch=64) as net:
         Hg = net.stage_dlt(g["dlt_offsets"].reshape(-1, 8))
         assert np.abs(Hg - g["dlt_H"]).max() < 2e-4           # fp32 torch.inverse noise (cond ~1.8e5)
