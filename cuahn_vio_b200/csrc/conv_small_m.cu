@@ -149,15 +149,33 @@ __global__ void __cluster_dims__(SMM_CLUSTER, 1, 1) __launch_bounds__(SMM_THREAD
 #pragma unroll
   for (int j = 0; j < SMM_CLUSTER; ++j) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote[j]) : "r"(s0), "r"(j));
   const int my_rows = (p.M - (int)rank + SMM_CLUSTER - 1) / SMM_CLUSTER;       // rows rank, rank + 8, ...
-  for (int idx = tid; idx < my_rows * (SMM_NSLAB / 2); idx += SMM_THREADS) {
+  // every remote load of this thread is issued before the first sum: one DSMEM round trip per thread instead of one per item
+  constexpr int ITEMS = (2 * MT * (SMM_NSLAB / 2) + SMM_THREADS - 1) / SMM_THREADS;     // ceil(rows per rank * column pairs / threads)
+  float2 part2[ITEMS][SMM_CLUSTER];
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int idx = tid + it * SMM_THREADS;
+    const bool on = idx < my_rows * (SMM_NSLAB / 2);
+    const int m = (int)rank + SMM_CLUSTER * (idx / (SMM_NSLAB / 2)), c = (idx % (SMM_NSLAB / 2)) * 2;
+#pragma unroll
+    for (int j = 0; j < SMM_CLUSTER; ++j) {
+      part2[it][j] = make_float2(0.f, 0.f);
+      if (on)
+        asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];"
+                     : "=f"(part2[it][j].x), "=f"(part2[it][j].y)
+                     : "r"(remote[j] + (uint32_t)(m * SMM_NSLAB + c) * 4));
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int idx = tid + it * SMM_THREADS;
+    if (idx >= my_rows * (SMM_NSLAB / 2)) break;
     const int m = (int)rank + SMM_CLUSTER * (idx / (SMM_NSLAB / 2)), c = (idx % (SMM_NSLAB / 2)) * 2;
     float v0 = 0.f, v1 = 0.f;
 #pragma unroll
     for (int j = 0; j < SMM_CLUSTER; ++j) {
-      float x0, x1;
-      asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(remote[j] + (uint32_t)(m * SMM_NSLAB + c) * 4));
-      v0 += x0;
-      v1 += x1;
+      v0 += part2[it][j].x;
+      v1 += part2[it][j].y;
     }
     v0 += __ldg(p.bias + n0 + c);
     v1 += __ldg(p.bias + n0 + c + 1);
