@@ -4,7 +4,8 @@
     python tools/sass_opcodes.py > profiles/r02_sass_opcodes.txt
 
 tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG/UTMASTG/UBLKCP, tcgen05.commit -> UTCBAR,
-TMEM alloc -> UTCATOMSWS / UTCALLOC-style ops, cp.async -> LDGSTS; legacy tensor path would show HMMA.
+TMEM alloc -> UTCATOMSWS / UTCALLOC-style ops, cp.async -> LDGSTS; texture gather -> TLD4, surface store -> SUST; the legacy
+tensor path (mma.sync -> HMMA, ldmatrix -> LDSM) is used by the batch-1 split-K kernel only.
 """
 import collections
 import os
@@ -15,7 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "cuahn_vio_b200", "lib", "libuahn.so")
 WATCH = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "UTCATOMSWS", "UTCCP", "LDGSTS",
-         "HMMA", "UCGABAR"]
+         "HMMA", "UCGABAR", "TLD4", "SUST", "LDSM"]
 
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 names = subprocess.run(["c++filt"], input="\n".join(re.findall(r"Function : (\S+)", sass)), capture_output=True, text=True).stdout.split("\n")

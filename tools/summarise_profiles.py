@@ -5,7 +5,8 @@
 
 The first argument is the launch list (`ncu --metrics gpu__time_duration.sum --csv --log-file …`), the second the
 `ncu -i prof.ncu-rep --page raw --csv` dump of the `--set full` capture of the same command.  Both hold the 26 launches
-of one 3-block step at 1024 pairs (tools/profile_step.py --batch 1024 --steps 2, -s 26 -c 26).
+of one 3-block step at 1024 pairs (tools/profile_step.py --batch 1024 --steps 2, -s 27 -c 26: one kernel zeroes the warp's cell array at create, 26 launches of
+the warm-up step are skipped).
 """
 import csv
 import json
@@ -71,7 +72,7 @@ def main():
     total = sum(x[3] for x in ls)
     with open(os.path.join(ROOT, "profiles", f"{rnd}_launches_step_b{pairs}.csv"), "w") as f:
         f.write(f"# ncu launch list — one 3-block UAHN step, {pairs} pairs, bf16 ({rnd}, final kernels: {DESC})\n")
-        f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 26 -c 26 --csv python "
+        f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 27 -c 26 --csv python "
                 f"tools/profile_step.py --batch {pairs} --steps 2\n")
         f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
         f.write("stage,kernel,grid,block,time_us,share\n")
@@ -89,7 +90,7 @@ def main():
     idx = {k: hdr.index(k) for k in FULL_KEYS}
     conv_bytes = 0.0
     with open(os.path.join(ROOT, "profiles", f"{rnd}_ncu_step_full_b{pairs}.csv"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -s 26 -c 26 python tools/profile_step.py --batch "
+        f.write("# ncu --set full --clock-control none --import-source on -s 27 -c 26 python tools/profile_step.py --batch "
                 f"{pairs} --steps 2  ({rnd}, final kernels; one 3-block step, {pairs} pairs, bf16)\n")
         f.write("# per-launch values are cold-cache and serialised: compare SHARES, not absolutes.  Units: us, MB, MB, % of "
                 "peak x3, MB (L2->SM), then % of peak\n")
