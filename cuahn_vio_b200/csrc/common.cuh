@@ -52,8 +52,9 @@ struct ConvGeom {
 // Every kernel of the forward is launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next
 // kernel's CTAs may become resident and run their prologue (barrier init, TMEM allocation, weight loads) while the
 // previous kernel drains, and block in pdl_wait() until its memory is visible.  Nothing produced by an earlier
-// kernel may be read, and nothing may be written to global memory, before pdl_wait().  Used on the small-batch latency path only (engine.cu: pdl_select);
-// UAHN_NO_PDL=1 disables it.
+// kernel may be read, and nothing may be written to global memory, before pdl_wait() — and EVERY kernel of the chain calls it,
+// even one that reads nothing from its predecessor: a grid that never waits could complete before the grid in front of it and
+// release its own dependents too early.  Used at every batch size (engine.cu: pdl_select); UAHN_NO_PDL=1 disables it.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -27,7 +27,13 @@ bool pdl_enabled() {
   static const bool allowed = getenv("UAHN_NO_PDL") == nullptr;
   return allowed && g_pdl_on;
 }
-void pdl_select(int n_pairs) { g_pdl_on = n_pairs <= 8; }
+// Every batch size (round 2; the first half of the round used it for <= 8 pairs only): with the next grid already resident in
+// the launch queue its CTAs start as SMs drain, which is worth 2-3 us per dependent kernel — 2 % of a 1024-pair call, 10 % of a
+// 256-pair call (0.748 -> 0.671 ms, same-box A/B).  UAHN_PDL_MAX_PAIRS=n restricts it to calls of at most n pairs.
+void pdl_select(int n_pairs) {
+  static const int max_pairs = getenv("UAHN_PDL_MAX_PAIRS") ? atoi(getenv("UAHN_PDL_MAX_PAIRS")) : (1 << 30);
+  g_pdl_on = n_pairs <= max_pairs;
+}
 }  // namespace uahn
 
 namespace {
