@@ -222,6 +222,106 @@ __global__ void __launch_bounds__(256) fc8_dlt_kernel(int n, const T* __restrict
   }
 }
 
+// Batch path (round 2): eight pairs per CTA.  A thread owns five 4-element slices of k (k = 4 (t + 256 i)): per slice eight
+// 16-byte weight loads serve 8 pairs x 8 outputs x 4 k = 256 FMAs, so the L2 -> SM weight traffic per pair halves against
+// fc8_dlt_kernel (4 pairs per CTA, scalar loads) and a thread waits for 5 batches of 16 wide loads instead of 20 trips of 12
+// scalar ones — the stage is a chain of L2 round trips, nothing else (16 us per launch at 1024 pairs, issue slots 23 % busy).
+// The 64 partial sums of a thread meet in shared memory ([output][thread], conflict-free) and are added in a fixed order.
+constexpr int FC8W_PAIRS = 8;
+constexpr size_t FC8W_SMEM = (size_t)FC8W_PAIRS * 8 * 257 * sizeof(float);
+template <typename T>
+__global__ void __launch_bounds__(256, 1) fc8_dlt_wide_kernel(int n, const T* __restrict__ feat, const float* __restrict__ W8,
+                                                             const float* __restrict__ b8, const float* __restrict__ Hprev,
+                                                             float* __restrict__ Hout, float* __restrict__ dout) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) float red_w[];              // [64][257]
+  __shared__ float d_s[FC8W_PAIRS][8];
+  const int pair0 = blockIdx.x * FC8W_PAIRS, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int np = min(FC8W_PAIRS, n - pair0);
+  float acc[FC8W_PAIRS][8];
+#pragma unroll
+  for (int p = 0; p < FC8W_PAIRS; ++p)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[p][o] = 0.f;
+#pragma unroll
+  for (int i = 0; i < FC_IN / (4 * 256); ++i) {
+    const int k = 4 * (tid + 256 * i);
+    float4 w[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) w[o] = __ldg(reinterpret_cast<const float4*>(W8 + o * FC_IN + k));
+    float x[FC8W_PAIRS][4];
+#pragma unroll
+    for (int p = 0; p < FC8W_PAIRS; ++p) {
+      const T* f = feat + (size_t)(pair0 + (p < np ? p : 0)) * FC_IN + k;      // (pairs past n re-read pair0; results dropped)
+      if constexpr (sizeof(T) == 2) {
+        const uint2 v = *reinterpret_cast<const uint2*>(f);
+        x[p][0] = __uint_as_float(v.x << 16); x[p][1] = __uint_as_float(v.x & 0xffff0000u);
+        x[p][2] = __uint_as_float(v.y << 16); x[p][3] = __uint_as_float(v.y & 0xffff0000u);
+      } else {
+        const float4 v = *reinterpret_cast<const float4*>(f);
+        x[p][0] = v.x; x[p][1] = v.y; x[p][2] = v.z; x[p][3] = v.w;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < FC8W_PAIRS; ++p)
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        acc[p][o] = fmaf(x[p][0], w[o].x, acc[p][o]);
+        acc[p][o] = fmaf(x[p][1], w[o].y, acc[p][o]);
+        acc[p][o] = fmaf(x[p][2], w[o].z, acc[p][o]);
+        acc[p][o] = fmaf(x[p][3], w[o].w, acc[p][o]);
+      }
+  }
+#pragma unroll
+  for (int p = 0; p < FC8W_PAIRS; ++p)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) red_w[(p * 8 + o) * 257 + tid] = acc[p][o];
+  __syncthreads();
+  {   // output tid / 4, quarter tid % 4 of the 256 partial sums, then the four quarters in lane order
+    const int po = tid >> 2, qt = tid & 3;
+    float v = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 64; ++j) v += red_w[po * 257 + qt * 64 + j];
+    const float v1 = __shfl_down_sync(0xffffffffu, v, 1), v2 = __shfl_down_sync(0xffffffffu, v, 2), v3 = __shfl_down_sync(0xffffffffu, v, 3);
+    if (qt == 0) {
+      const float sum = ((v + v1) + v2) + v3 + b8[po & 7];
+      d_s[po >> 3][po & 7] = sum;
+      if (dout && (po >> 3) < np) dout[(pair0 + (po >> 3)) * 8 + (po & 7)] = sum;
+    }
+  }
+  __syncthreads();
+  if (wid < np) {                       // one warp per pair: DLT + composition
+    const int pair = pair0 + wid;
+    float dst[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x, y;
+      corner(i, x, y);
+      dst[2 * i] = __fadd_rn(x, d_s[wid][2 * i]);
+      dst[2 * i + 1] = __fadd_rn(y, d_s[wid][2 * i + 1]);
+    }
+    double h[9];
+    dlt_warp(dst, h);
+    if (lane == 0) {
+      float hb[9], out[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) hb[i] = (float)h[i];
+      if (Hprev) {
+        float hp[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) hp[i] = Hprev[pair * 9 + i];
+        mat3_mul(hp, hb, out);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) out[i] = hb[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Hout[pair * 9 + i] = out[i];
+    }
+  }
+}
+
 // Latency path (<= FC8_SMALL_MAX pairs): the same stage with the 5120-long dot products split over a cluster of 8 CTAs per
 // pair (640 k each, 8 x fewer dependent L2 round trips per thread), partial sums reduced through distributed shared
 // memory into rank 0, which adds the bias and runs the DLT + composition.  (One CTA per 4 pairs takes 20 us at batch 1.)
@@ -742,7 +842,12 @@ cudaError_t launch_fc8_dlt(int n, const T* feat, const float* W8, const float* b
                            float* dout, cudaStream_t st) {
   if (n <= FC8_SMALL_MAX)   // latency path: a cluster of 8 CTAs per pair (compile-time cluster dimensions)
     return launch_pdl(fc8_dlt_cluster_kernel<T>, dim3(FC8_CLUSTER * n), dim3(256), 0, st, n, feat, W8, b8, Hprev, Hout, dout);
-  return launch_pdl(fc8_dlt_kernel<T>, dim3((n + FC8_PAIRS - 1) / FC8_PAIRS), dim3(256), 0, st, n, feat, W8, b8, Hprev, Hout, dout);
+  static const bool narrow = getenv("UAHN_FC8_NARROW") != nullptr;      // A/B: the 4-pairs-per-CTA kernel
+  if (narrow)
+    return launch_pdl(fc8_dlt_kernel<T>, dim3((n + FC8_PAIRS - 1) / FC8_PAIRS), dim3(256), 0, st, n, feat, W8, b8, Hprev, Hout, dout);
+  static SmemOptIn optin;   // per device (common.cuh)
+  if (cudaError_t e = optin.ensure(fc8_dlt_wide_kernel<T>, FC8W_SMEM); e != cudaSuccess) return e;
+  return launch_pdl(fc8_dlt_wide_kernel<T>, dim3((n + FC8W_PAIRS - 1) / FC8W_PAIRS), dim3(256), FC8W_SMEM, st, n, feat, W8, b8, Hprev, Hout, dout);
 }
 template cudaError_t launch_fc8_dlt<float>(int, const float*, const float*, const float*, const float*, float*, float*,
                                            cudaStream_t);
