@@ -719,6 +719,9 @@ int uahn_create(const uahn_config* cfg, uahn_handle** out) {
 
 void uahn_destroy(uahn_handle* h) {
   if (!h) return;
+  int prev_dev = -1;                       // the array / texture / surface objects belong to the handle's device
+  cudaGetDevice(&prev_dev);
+  cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
   warp_cells_destroy(h->cells);
@@ -733,6 +736,7 @@ void uahn_destroy(uahn_handle* h) {
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  if (prev_dev >= 0) cudaSetDevice(prev_dev);
 }
 
 const char* uahn_last_error(const uahn_handle* h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
