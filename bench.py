@@ -561,7 +561,8 @@ def run_ours(args):
         "stage_ms_per_step": {"warp_concat_pool": warp_ms_per_step, "conv_stacks": prof_ms[1] / Kp,
                               "mc_head_gemm": prof_ms[2] / Kp, "fc_dlt_mc_small": prof_ms[3] / Kp},
         "stage_launches_per_step": {k: int(v // Kp) for k, v in zip(("warp", "conv", "mc_gemm", "small"), prof_cnt)},
-        "hbm": {"kernel": f"warp+concat+pool (3 launches per call, {calls_per_step} call(s) per step)",
+        "hbm": {"kernel": f"warp+concat+pool (3 texture-gather launches + the cell-array fill per call, {calls_per_step} call(s) per step; "
+                          "the fill's time is inside, only the 3 warps are credited)",
                 "algorithmic_bytes_per_step": 3 * WARP_BYTES * B,
                 "achieved_gbs": (3 * WARP_BYTES * B / (warp_ms_per_step * 1e-3) / 1e9) if warp_ms_per_step > 0 else None,
                 "peak_gbs": peaks["hbm_gbs"], "layout": "fp32 in/out as in the reference (573 440 B per warp)"},

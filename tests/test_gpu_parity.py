@@ -487,6 +487,26 @@ def test_texture_warp_matches_shared_memory_warp(api, wfile):
     assert np.abs(outs[True][0] - outs[False][0]).max() < BF16_PX
 
 
+def test_texture_warp_sees_every_refill_of_the_cell_array(api, wfile):
+    """The cell array is rewritten by every batch call and read through the (non-coherent) texture path, with programmatic
+    dependent launch between the kernels: alternate two input sets through one handle — every call must reproduce the first
+    result of its set bit for bit (a stale texture line or a fill / gather overlap would not)."""
+    n = 40
+    sets = [S.synthetic_batch(n, start=700), S.synthetic_batch(n, start=760)]
+    with api.Uahn(wfile, "prior3", precision="bf16", max_batch=n) as net:
+        first = {}
+        for it in range(8):
+            k = it & 1
+            prev, curr, _, prior = sets[k]
+            m, c, _ = net.infer_batch(prev, curr, prior, seed=9)
+            x4 = net.debug_read("x4", (n, 2, 224, 320))
+            if k not in first:
+                first[k] = (m.copy(), c.copy(), x4.copy())
+            else:
+                assert np.array_equal(m, first[k][0]) and np.array_equal(c, first[k][1]) and np.array_equal(x4, first[k][2]), it
+        assert not np.array_equal(first[0][2], first[1][2])
+
+
 def test_cta_pair_deep_layers_match_single_cta_kernels(api, wfile):
     """Deep conv layers (Cin % 64 == 0) at a batch large enough for the CTA-pair kernels (tcgen05.mma.cta_group::2, half
     of each B stage per CTA) vs the one-CTA im2col kernels: the same accumulation order, so every activation and output
