@@ -103,3 +103,32 @@ def test_transfer_identity():
     p2, cov = O.transfer_mean_var_single(var, torch.eye(3).unsqueeze(0), pts)
     for i in range(4):
         assert torch.allclose(cov[0, i], torch.diag(var[0, i]))
+
+
+def test_dlt_closed_form_of_the_fixed_rectangle_equals_the_linear_solve(golden_stages):
+    """The product path's DLT (head_kernels.cu dlt_rect) is the square-to-quadrilateral mapping composed with the frame's
+    scaling, because the four source points are always the frame corners (model_to_trace.py:78-83).  Restated here in numpy
+    and held against the oracle's 8x8 solve (model_to_trace.py:42-61) in fp64, and against the reference-made fixture."""
+    def dlt_rect(dst):                       # dst [4, 2] in the model's corner order UL, BL, BR, UR
+        (x0, y0), (x3, y3), (x2, y2), (x1, y1) = dst
+        dx1, dx2, dy1, dy2 = x1 - x2, x3 - x2, y1 - y2, y3 - y2
+        sx, sy = (x0 - x1) + (x2 - x3), (y0 - y1) + (y2 - y3)
+        inv = 1.0 / (dx1 * dy2 - dy1 * dx2)
+        g, k = (sx * dy2 - sy * dx2) * inv, (dx1 * sy - dy1 * sx) * inv
+        iw, ih = 1.0 / 319.0, 1.0 / 223.0
+        return np.array([[((x1 - x0) + g * x1) * iw, ((x3 - x0) + k * x3) * ih, x0],
+                         [((y1 - y0) + g * y1) * iw, ((y3 - y0) + k * y3) * ih, y0],
+                         [g * iw, k * ih, 1.0]])
+
+    pts0 = O.origin_4pt().unsqueeze(0).double()
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        off = (rng.random((1, 4, 2)) * 2 - 1) * 40
+        ref = O.dlt_solve(pts0, pts0 + torch.from_numpy(off))[0].numpy()
+        got = dlt_rect((pts0 + torch.from_numpy(off))[0].numpy())
+        assert np.abs(got - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+    assert np.array_equal(dlt_rect(pts0[0].numpy()), np.eye(3))          # DLT(p, p) = I exactly
+    g = golden_stages                                                     # the reference's own fp32 torch.inverse results
+    for off, href in zip(g["dlt_offsets"].reshape(-1, 4, 2), g["dlt_H"]):
+        got = dlt_rect(pts0[0].numpy() + off.astype(np.float64))
+        assert np.abs(got - href).max() < 2e-4
