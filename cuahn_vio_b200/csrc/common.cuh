@@ -57,6 +57,13 @@ struct ConvGeom {
 // release its own dependents too early.  Used at every batch size (engine.cu: pdl_select); UAHN_NO_PDL=1 disables it.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Grids that fit the machine in one wave (the latency path: 28-CTA warp bands, 32-CTA split-K clusters) let their dependents
+// start right away — the next kernel's prologue (barrier init, TMEM allocation, weight prefetch) then overlaps this grid
+// instead of starting when its last CTA exits.  Many-wave grids keep the implicit trigger at exit: early dependents would hold
+// SM resources that their own later CTAs still need.
+__device__ __forceinline__ void pdl_launch_dependents_if_single_wave() {
+  if (gridDim.x * gridDim.y * gridDim.z <= 128) pdl_launch_dependents();
+}
 
 #ifdef __CUDACC__
 // ---- per-device host-side caches ----------------------------------------------------------------------------

@@ -78,6 +78,7 @@ __global__ void __cluster_dims__(SMM_CLUSTER, 1, 1) __launch_bounds__(SMM_THREAD
     rowoff[r] = (uint32_t)(img * p.in_pitch_n_b + (long long)(oy * p.stride) * p.in_pitch_y_b + (long long)(ox * p.stride) * p.cin_b);
   }
   pdl_wait();                                                   // the input comes from the previous layer
+  pdl_launch_dependents();                                      // 16-32 CTAs: the next kernel's prologue overlaps this one
   __syncthreads();
   const uint8_t* in0 = p.in + p.in_origin_b;
 #pragma unroll
