@@ -529,8 +529,8 @@ __global__ void __launch_bounds__(256) mc_fc1_small_fused_kernel(const __nv_bflo
                                                                   __nv_bfloat16* __restrict__ hid,
                                                                   const uint8_t* __restrict__ keep_masks, uint64_t seed,
                                                                   uint64_t first_pair, const uint64_t* __restrict__ rng_dev) {
-  pdl_wait();
-  pdl_launch_dependents();
+  // the keep bytes depend on (seed, pair) only — uploaded in front of the whole chain — so the whole mask phase runs BEFORE
+  // griddepcontrol.wait, next to the last conv layer; only the feature needs the previous kernel
   if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }
   __shared__ float part[8][MC][FC1S_JT];
   __shared__ __align__(16) uint8_t s_bits[(FC_IN / 8) * MC];      // 10 KB
@@ -560,6 +560,8 @@ __global__ void __launch_bounds__(256) mc_fc1_small_fused_kernel(const __nv_bflo
       for (int qd = 0; qd < 4; ++qd) s_bits[(k32 * 4 + qd) * MC + smp] = (uint8_t)b[qd];
     }
   }
+  pdl_wait();
+  pdl_launch_dependents();
   __syncthreads();
   const uint4* f4 = reinterpret_cast<const uint4*>(feat + (size_t)pair * FC_IN);
   const uint4* w4 = reinterpret_cast<const uint4*>((head ? Wu : Wm) + (size_t)j0 * FC_IN);
@@ -718,8 +720,8 @@ __global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid
                                                         const uint8_t* __restrict__ keep_masks, uint64_t seed,
                                                         uint64_t first_pair, const uint64_t* __restrict__ rng_dev,
                                                         HeadOut o) {
-  pdl_wait();
-  pdl_launch_dependents();
+  // before griddepcontrol.wait: everything that does not come from the previous kernel (the second-layer weights; the rng
+  // block was uploaded in front of the whole chain, and every kernel of the chain has waited on its predecessor)
   if (rng_dev) { seed = rng_dev[0]; first_pair = rng_dev[1]; }
   __shared__ __align__(16) float w2[2][8][FC_HID + 4];   // +4 floats: the 8 output rows hit 8 different bank groups
   __shared__ float outv[2][MC][8];
@@ -729,6 +731,8 @@ __global__ void __launch_bounds__(256) mc_final_kernel(const T* __restrict__ hid
     w2[0][i / FC_HID][i % FC_HID] = W2m[i];
     w2[1][i / FC_HID][i % FC_HID] = W2u[i];
   }
+  pdl_wait();
+  pdl_launch_dependents();
   __syncthreads();
   {
     const int head = tid >> 7, s = (tid >> 3) & 15, oo = tid & 7;
