@@ -330,8 +330,6 @@ template <typename T>
 __global__ void __cluster_dims__(FC8_CLUSTER, 1, 1) __launch_bounds__(256)
     fc8_dlt_cluster_kernel(int n, const T* __restrict__ feat, const float* __restrict__ W8, const float* __restrict__ b8,
                            const float* __restrict__ Hprev, float* __restrict__ Hout, float* __restrict__ dout) {
-  pdl_wait();
-  pdl_launch_dependents();
   __shared__ float part[8][8];
   __shared__ float red[FC8_CLUSTER][8];     // rank 0's copy collects every rank's partial sums
   __shared__ float d_s[8];
@@ -339,18 +337,29 @@ __global__ void __cluster_dims__(FC8_CLUSTER, 1, 1) __launch_bounds__(256)
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x / FC8_CLUSTER;
   constexpr int KPER = FC_IN / FC8_CLUSTER;   // 640
+  constexpr int TRIPS = (KPER + 255) / 256;
   const int k0 = (int)rank * KPER;
+  // this thread's 8 x 3 weights are requested before griddepcontrol.wait: only the feature comes from the previous kernel
+  float w[TRIPS][8];
+#pragma unroll
+  for (int i = 0; i < TRIPS; ++i) {
+    const int k = k0 + min(tid + 256 * i, KPER - 1);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) w[i][o] = __ldg(W8 + o * FC_IN + k);
+  }
+  pdl_wait();
+  pdl_launch_dependents();
   float acc[8];
 #pragma unroll
   for (int o = 0; o < 8; ++o) acc[o] = 0.f;
 #pragma unroll
-  for (int i = 0; i < (KPER + 255) / 256; ++i) {
+  for (int i = 0; i < TRIPS; ++i) {
     const int kk = tid + 256 * i;
     if (kk < KPER) {
       const int k = k0 + kk;
       const float x = to_f32<T>(feat[(size_t)pair * FC_IN + k]);
 #pragma unroll
-      for (int o = 0; o < 8; ++o) acc[o] = fmaf(x, __ldg(W8 + o * FC_IN + k), acc[o]);
+      for (int o = 0; o < 8; ++o) acc[o] = fmaf(x, w[i][o], acc[o]);
     }
   }
 #pragma unroll
